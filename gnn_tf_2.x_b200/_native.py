@@ -1,0 +1,211 @@
+# coding=utf-8
+"""ctypes binding of ``libgnn_b200.so`` (C ABI declared in ``include/gnn_b200.h``).
+
+PyTorch is used only as the owner of device memory and streams: every call hands raw device pointers
+(``tensor.data_ptr()``) and the current CUDA stream to the library.  There is NO fallback: if the shared library is
+missing, or no CUDA device is present, the functions raise ``RuntimeError``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import numpy as np
+import torch
+
+GNN_MAX_LAYERS = 4
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'libgnn_b200.so')
+_lib: Optional[C.CDLL] = None
+
+ACT_CODES = {'linear': 0, 'relu': 1, 'tanh': 2, 'sigmoid': 3, 'selu': 4, 'elu': 5, 'softmax': 6, 'softplus': 7}
+
+
+class gnn_mlp(C.Structure):
+    _fields_ = [('n_layers', C.c_int32),
+                ('dims', C.c_int32 * (GNN_MAX_LAYERS + 1)),
+                ('act', C.c_int32 * GNN_MAX_LAYERS),
+                ('W', C.c_void_p * GNN_MAX_LAYERS),
+                ('b', C.c_void_p * GNN_MAX_LAYERS),
+                ('drop_rate', C.c_float * (GNN_MAX_LAYERS + 1)),
+                ('has_bn', C.c_int32),
+                ('bn_gamma', C.c_void_p), ('bn_beta', C.c_void_p),
+                ('bn_moving_mean', C.c_void_p), ('bn_moving_var', C.c_void_p),
+                ('bn_eps', C.c_float), ('bn_momentum', C.c_float)]
+
+
+class gnn_mlp_grad(C.Structure):
+    _fields_ = [('dW', C.c_void_p * GNN_MAX_LAYERS), ('db', C.c_void_p * GNN_MAX_LAYERS),
+                ('dgamma', C.c_void_p), ('dbeta', C.c_void_p)]
+
+
+class gnn_graph(C.Structure):
+    _fields_ = [('n_nodes', C.c_int64), ('n_arcs', C.c_int64),
+                ('rowptr', C.c_void_p), ('col', C.c_void_p), ('val', C.c_void_p), ('row_scale', C.c_void_p),
+                ('rowptr_T', C.c_void_p), ('col_T', C.c_void_p), ('val_T', C.c_void_p)]
+
+
+class gnn_loop_args(C.Structure):
+    _fields_ = [('D', C.c_int32), ('NL_self', C.c_int32), ('NL_agg', C.c_int32), ('AL', C.c_int32),
+                ('x0', C.c_void_p), ('nodes', C.c_void_p), ('agg_nodes', C.c_void_p), ('agg_arcs', C.c_void_p),
+                ('max_iter', C.c_int32), ('threshold', C.c_float), ('training', C.c_int32),
+                ('save_for_backward', C.c_int32), ('seed', C.c_uint32),
+                ('x_out', C.c_void_p), ('k_out', C.c_void_p)]
+
+
+# every symbol include/gnn_b200.h declares (tests check that the library exports all of them)
+EXPORTED_SYMBOLS = ['gnn_last_error', 'gnn_abi_version', 'gnn_device_info', 'gnn_csr_build', 'gnn_spmm',
+                    'gnn_state_loop_workspace_bytes', 'gnn_state_loop_forward', 'gnn_state_loop_backward',
+                    'gnn_launch_count']
+
+
+def library_path() -> str: return _LIB_PATH
+
+
+def lib() -> C.CDLL:
+    """ load the shared library once; loud failure when it has not been built """
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            raise RuntimeError(f'{_LIB_PATH} is missing: build it with `python -c "import __graft_entry__ as g; g.build()"` '
+                               f'(make -C gnn_tf_2.x_b200/csrc). There is no CPU fallback.')
+        l = C.CDLL(_LIB_PATH)
+        l.gnn_last_error.restype = C.c_char_p
+        l.gnn_abi_version.restype = C.c_int
+        l.gnn_launch_count.restype = C.c_int64
+        l.gnn_launch_count.argtypes = [C.c_int32]
+        l.gnn_device_info.argtypes = [C.POINTER(C.c_int32)] * 4
+        l.gnn_csr_build.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64,
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.POINTER(C.c_int32), C.c_void_p, C.POINTER(C.c_size_t), C.c_void_p]
+        l.gnn_spmm.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32,
+                               C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]
+        l.gnn_state_loop_workspace_bytes.argtypes = [C.POINTER(gnn_graph), C.POINTER(gnn_mlp), C.POINTER(gnn_loop_args),
+                                                     C.POINTER(C.c_size_t)]
+        l.gnn_state_loop_forward.argtypes = [C.POINTER(gnn_graph), C.POINTER(gnn_mlp), C.POINTER(gnn_loop_args),
+                                             C.c_void_p, C.c_size_t, C.c_void_p]
+        l.gnn_state_loop_backward.argtypes = [C.POINTER(gnn_graph), C.POINTER(gnn_mlp), C.POINTER(gnn_loop_args), C.c_void_p,
+                                              C.POINTER(gnn_mlp_grad), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                              C.c_void_p, C.c_size_t, C.c_void_p]
+        for name in ('gnn_device_info', 'gnn_csr_build', 'gnn_spmm', 'gnn_state_loop_workspace_bytes',
+                     'gnn_state_loop_forward', 'gnn_state_loop_backward'):
+            getattr(l, name).restype = C.c_int
+        _lib = l
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise RuntimeError(f'{what} failed ({rc}): {lib().gnn_last_error().decode()}')
+
+
+def default_device() -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError('gnn_b200 needs a CUDA device (B200, sm_100a): there is no CPU path')
+    return torch.device('cuda', torch.cuda.current_device())
+
+
+def _stream(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def launch_count(reset: bool = False) -> int:
+    return int(lib().gnn_launch_count(1 if reset else 0))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def csr_from_coo_transposed(coo, *, device=None, with_transpose: bool = False):
+    """ GraphTensor.COO2SparseTransposedTensor (graph_class.py:364-372) on the GPU: the COO matrix is transposed
+    (new row = coo.col) and stored row-major, entries sorted by (row, col), ties in input order. """
+    from .graph_class import SparseCSR
+    device = default_device() if device is None else torch.device(device)
+    rows = torch.as_tensor(np.ascontiguousarray(coo.col, dtype=np.int32), device=device)
+    cols = torch.as_tensor(np.ascontiguousarray(coo.row, dtype=np.int32), device=device)
+    vals = torch.as_tensor(np.ascontiguousarray(coo.data, dtype=np.float32), device=device)
+    n_rows, n_cols = int(coo.shape[1]), int(coo.shape[0])
+    return csr_build(rows, cols, vals, n_rows, n_cols, with_transpose=with_transpose)
+
+
+def csr_build(rows: torch.Tensor, cols: torch.Tensor, vals: torch.Tensor, n_rows: int, n_cols: int, *,
+              with_transpose: bool = False):
+    """ gnn_csr_build on device int32/float32 tensors """
+    from .graph_class import SparseCSR
+    l = lib()
+    device = rows.device
+    if device.type != 'cuda': raise RuntimeError('csr_build needs CUDA tensors')
+    nnz = int(rows.shape[0])
+    i32 = lambda n: torch.empty(max(n, 1), dtype=torch.int32, device=device)
+    f32 = lambda n: torch.empty(max(n, 1), dtype=torch.float32, device=device)
+    rowptr, col_s, val_s, perm, row_scale = i32(n_rows + 1), i32(nnz), f32(nnz), i32(nnz), f32(n_rows)
+    rowptr_T = col_T = perm_T = val_T = None
+    if with_transpose: rowptr_T, col_T, perm_T, val_T = i32(n_cols + 1), i32(nnz), i32(nnz), f32(nnz)
+    uniform = C.c_int32(0)
+    ws_bytes = C.c_size_t(0)
+    with torch.cuda.device(device):
+        args = [_ptr(rows), _ptr(cols), _ptr(vals), nnz, n_rows, n_cols, _ptr(rowptr), _ptr(col_s), _ptr(val_s), _ptr(perm),
+                _ptr(row_scale), _ptr(rowptr_T), _ptr(col_T), _ptr(perm_T), _ptr(val_T), C.byref(uniform)]
+        check(l.gnn_csr_build(*args, None, C.byref(ws_bytes), _stream(device)), 'gnn_csr_build(size query)')
+        ws = torch.empty(ws_bytes.value, dtype=torch.uint8, device=device)
+        check(l.gnn_csr_build(*args, _ptr(ws), C.byref(ws_bytes), _stream(device)), 'gnn_csr_build')
+    trim = lambda t, n: None if t is None else t[:n]
+    return SparseCSR(rowptr[:n_rows + 1], trim(col_s, nnz), trim(val_s, nnz), trim(perm, nnz), (n_rows, n_cols),
+                     rowptr_T=trim(rowptr_T, n_cols + 1), col_T=trim(col_T, nnz), perm_T=trim(perm_T, nnz),
+                     values_T=trim(val_T, nnz), row_scale=row_scale[:n_rows] if uniform.value else None)
+
+
+def spmm(rowptr: torch.Tensor, col: torch.Tensor, val: Optional[torch.Tensor], dense: torch.Tensor,
+         out: Optional[torch.Tensor] = None, accumulate: bool = False) -> torch.Tensor:
+    """ out[r] = sum_e val[e] * dense[col[e]] over the stored entries of row r (gnn_spmm) """
+    l = lib()
+    device = dense.device
+    dense = dense.contiguous()
+    n_rows, F = int(rowptr.shape[0]) - 1, int(dense.shape[1])
+    if out is None: out = torch.empty((n_rows, F), dtype=torch.float32, device=device)
+    with torch.cuda.device(device):
+        check(l.gnn_spmm(_ptr(rowptr), _ptr(col), _ptr(val), n_rows, _ptr(dense), dense.stride(0) if F else 0, F, _ptr(out),
+                         out.stride(0) if F else 0, 1 if accumulate else 0, _stream(device)), 'gnn_spmm')
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def make_graph(adj) -> gnn_graph:
+    """ gnn_graph view of a SparseCSR (Adjacency^T); uses the per-row weight when every row is uniform """
+    g = gnn_graph()
+    g.n_nodes, g.n_arcs = adj.dense_shape[0], adj.nnz
+    g.rowptr, g.col = _ptr(adj.rowptr), _ptr(adj.col)
+    if adj.row_scale is not None:
+        g.val, g.row_scale, g.val_T = None, _ptr(adj.row_scale), None
+    else:
+        g.val, g.row_scale, g.val_T = _ptr(adj.values), None, _ptr(adj.values_T)
+    g.rowptr_T, g.col_T = _ptr(adj.rowptr_T), _ptr(adj.col_T)
+    return g
+
+
+def make_mlp(spec, keepalive: list) -> gnn_mlp:
+    """ gnn_mlp view of a keras_compat.MLPSpec; tensors that must outlive the call are appended to keepalive """
+    m = gnn_mlp()
+    L = spec.n_layers
+    if L > GNN_MAX_LAYERS: raise NotImplementedError(f'at most {GNN_MAX_LAYERS} Dense layers per MLP are supported, got {L}')
+    if spec.alpha_dropout and spec.has_dropout: raise NotImplementedError('AlphaDropout is not implemented in the CUDA path')
+    m.n_layers = L
+    for i, d in enumerate(spec.dims): m.dims[i] = int(d)
+    for i in range(L):
+        if spec.activations[i] not in ACT_CODES: raise NotImplementedError(f'activation {spec.activations[i]!r} not implemented')
+        m.act[i] = ACT_CODES[spec.activations[i]]
+        w = spec.dense_layers[i].kernel.detach().contiguous()
+        b = spec.dense_layers[i].bias.detach().contiguous()
+        keepalive += [w, b]
+        m.W[i], m.b[i] = w.data_ptr(), b.data_ptr()
+    for i in range(L + 1): m.drop_rate[i] = float(spec.dropout_rates[i])
+    bn = spec.batchnorm
+    m.has_bn = 0 if bn is None else 1
+    if bn is not None:
+        m.bn_gamma, m.bn_beta = bn.gamma.data_ptr(), bn.beta.data_ptr()
+        m.bn_moving_mean, m.bn_moving_var = bn.moving_mean.data_ptr(), bn.moving_variance.data_ptr()
+        m.bn_eps, m.bn_momentum = bn.epsilon, bn.momentum
+    return m

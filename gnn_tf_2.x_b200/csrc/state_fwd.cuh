@@ -1,0 +1,362 @@
+// state_fwd.cuh -- the fused forward iteration kernel of the state-convergence loop (sm_100a).
+//
+// One launch = one iteration t of the reference's while_loop body + the condition for t+1
+// (GNN/GNN.py:223-242 and :202-220).  Per tile of TN nodes a CTA
+//   1. stages the tile's row pointers and arc (source) indices in shared memory (coalesced),
+//   2. GATHER: LPN = DP/4 adjacent lanes own one destination node; each lane pulls 16 bytes of every incoming
+//      source row with 128-bit read-only loads, accumulating the segment sum in registers in stored (ascending
+//      source) order -- no atomics, deterministic; own state row and the per-node constant row are loaded the
+//      same way; everything lands in a shared-memory tile [TN][SA] = [state | agg | cst],
+//   3. MLP: Dense layers as register-blocked (8 nodes x 4 units per thread) FMA loops over the tile, weights
+//      in shared memory (staged once per CTA), bias + activation (+ dropout) fused,
+//   4. EPILOGUE: final affine (BatchNormalization in inference mode), 128-bit coalesced store of the new state,
+//      per-node test ||x_new - x|| > thr * ||x|| reduced by shuffles over the node's lanes and a ballot per
+//      warp into one atomicOr on the device flag of iteration t+1.
+// The kernel starts by reading the flag of iteration t and returns at once when the loop has already
+// stopped, so the host can enqueue max_iter launches without ever synchronising.
+#pragma once
+#include "net_layout.cuh"
+
+namespace gnn {
+
+struct IterParams {
+    // graph (destination-sorted CSR)
+    const int32_t* rowptr;
+    const int32_t* col;
+    const float* val;        // NULL => row scale in cst[:, C]
+    long long N;
+    // state
+    const float* x_in;       // [N, DP]
+    float* x_out;            // [N, DP]  (pre-BN output h_t when bn_train)
+    float* agg_save;         // [N, DP] or NULL
+    const float* cst;        // [N, CP]
+    const float* wpack;      // packed net
+    // loop control
+    const int* go_cur;       // flag of this iteration
+    int* go_next;            // flag of the next one (NULL: do not test)
+    int* k_ptr;
+    int t;
+    float thr;
+    double* bn_partial;      // [gridDim.x][2][DP] when bn_train
+    int bn_train;
+    uint32_t seed;
+    int training;
+    int scol_cap;
+    NetLayout net;
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// register-blocked dense layer over a shared-memory tile: out[n, j] = sum_k in[n, k] * W[k, j]
+// thread micro-tile: 8 nodes (ng + NG*i) x 4 units (4cg .. 4cg+3)
+// ---------------------------------------------------------------------------------------------------------
+template <int TN>
+__device__ __forceinline__ void dense_micro(const float* __restrict__ inb, int row_step, int K,
+                                            const float* __restrict__ wb, int HP, float (&acc)[8][4]) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
+#pragma unroll 2
+    for (int k = 0; k < K; k += 4) {
+        const float4 w0 = ld4(wb + (k + 0) * HP);
+        const float4 w1 = ld4(wb + (k + 1) * HP);
+        const float4 w2 = ld4(wb + (k + 2) * HP);
+        const float4 w3 = ld4(wb + (k + 3) * HP);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float4 a = ld4(inb + i * row_step + k);
+            acc[i][0] = fmaf(a.x, w0.x, acc[i][0]); acc[i][1] = fmaf(a.x, w0.y, acc[i][1]);
+            acc[i][2] = fmaf(a.x, w0.z, acc[i][2]); acc[i][3] = fmaf(a.x, w0.w, acc[i][3]);
+            acc[i][0] = fmaf(a.y, w1.x, acc[i][0]); acc[i][1] = fmaf(a.y, w1.y, acc[i][1]);
+            acc[i][2] = fmaf(a.y, w1.z, acc[i][2]); acc[i][3] = fmaf(a.y, w1.w, acc[i][3]);
+            acc[i][0] = fmaf(a.z, w2.x, acc[i][0]); acc[i][1] = fmaf(a.z, w2.y, acc[i][1]);
+            acc[i][2] = fmaf(a.z, w2.z, acc[i][2]); acc[i][3] = fmaf(a.z, w2.w, acc[i][3]);
+            acc[i][0] = fmaf(a.w, w3.x, acc[i][0]); acc[i][1] = fmaf(a.w, w3.y, acc[i][1]);
+            acc[i][2] = fmaf(a.w, w3.z, acc[i][2]); acc[i][3] = fmaf(a.w, w3.w, acc[i][3]);
+        }
+    }
+}
+
+// all micro-tiles of one layer; epi(ng, cg, acc) consumes the accumulators (no barrier inside)
+template <int TN, int NT, typename Epilogue>
+__device__ __forceinline__ void dense_tile(const float* __restrict__ in, int in_stride, int K,
+                                           const float* __restrict__ W, int HP, Epilogue epi) {
+    constexpr int NG = TN / 8;
+    const int CG = HP >> 2;
+    for (int mt = threadIdx.x; mt < NG * CG; mt += NT) {
+        const int cg = mt % CG, ng = mt / CG;
+        float acc[8][4];
+        dense_micro<TN>(in + ng * in_stride, NG * in_stride, K, W + 4 * cg, HP, acc);
+        epi(ng, cg, acc);
+    }
+}
+
+// segment sum of the incoming source rows of one node; STAGED: indices / weights come from shared memory
+template <int DP, bool HAS_VAL, bool STAGED>
+__device__ __forceinline__ float4 gather_rows(const float* __restrict__ x_in, int lane_off, int e0, int e1,
+                                              const int32_t* __restrict__ cols, const float* __restrict__ vals) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int e = e0;
+    for (; e + 4 <= e1; e += 4) {
+        int s0, s1, s2, s3;
+        if (STAGED) { s0 = cols[e]; s1 = cols[e + 1]; s2 = cols[e + 2]; s3 = cols[e + 3]; }
+        else { s0 = __ldg(cols + e); s1 = __ldg(cols + e + 1); s2 = __ldg(cols + e + 2); s3 = __ldg(cols + e + 3); }
+        const float4 r0 = ldg4(x_in + (size_t)s0 * DP + lane_off);
+        const float4 r1 = ldg4(x_in + (size_t)s1 * DP + lane_off);
+        const float4 r2 = ldg4(x_in + (size_t)s2 * DP + lane_off);
+        const float4 r3 = ldg4(x_in + (size_t)s3 * DP + lane_off);
+        if (HAS_VAL) {
+            float w0, w1, w2, w3;
+            if (STAGED) { w0 = vals[e]; w1 = vals[e + 1]; w2 = vals[e + 2]; w3 = vals[e + 3]; }
+            else { w0 = __ldg(vals + e); w1 = __ldg(vals + e + 1); w2 = __ldg(vals + e + 2); w3 = __ldg(vals + e + 3); }
+            acc = fma4(w0, r0, acc); acc = fma4(w1, r1, acc); acc = fma4(w2, r2, acc); acc = fma4(w3, r3, acc);
+        } else {
+            acc = add4(acc, r0); acc = add4(acc, r1); acc = add4(acc, r2); acc = add4(acc, r3);
+        }
+    }
+    for (; e < e1; ++e) {
+        const int s = STAGED ? cols[e] : __ldg(cols + e);
+        const float4 r = ldg4(x_in + (size_t)s * DP + lane_off);
+        if (HAS_VAL) acc = fma4(STAGED ? vals[e] : __ldg(vals + e), r, acc);
+        else acc = add4(acc, r);
+    }
+    return acc;
+}
+
+__device__ __forceinline__ float drop1(float v, bool active, uint32_t key, uint64_t idx, float rate, float scale) {
+    if (!active) return v;
+    return dropout_keep(key, idx, rate) ? v * scale : 0.f;
+}
+
+template <int DP, bool HAS_VAL, int TN, int NT>
+__global__ void __launch_bounds__(NT) state_iter_kernel(const IterParams p) {
+    static_assert(TN % 32 == 0 && NT % 32 == 0 && TN % 8 == 0, "tile shape");
+    constexpr int LPN = DP / 4;          // lanes per node row
+    constexpr int NGRP = NT / LPN;       // node rows gathered concurrently by a CTA
+    static_assert(LPN >= 1 && LPN <= 32 && NT % LPN == 0, "lane mapping");
+
+    if (*reinterpret_cast<const volatile int*>(p.go_cur) == 0) return;  // loop already stopped (uniform)
+
+    const NetLayout& net = p.net;
+    const int tid = threadIdx.x;
+    const int SA = net.SA, SB = net.SB, CP = net.CP, KP = net.KP, D = net.D;
+
+    extern __shared__ __align__(16) float smem[];
+    float* sW = smem;
+    float* bufA = sW + net.fwd_floats;
+    float* bufB = bufA + TN * SA;
+    int* srow = reinterpret_cast<int*>(bufB + TN * SB);
+    int* scol = srow + ((TN + 1 + 3) & ~3);
+    float* sval = reinterpret_cast<float*>(scol + p.scol_cap);
+    __shared__ int s_flag;
+
+    for (int i = tid * 4; i < net.fwd_floats; i += NT * 4) st4(sW + i, ldg4(p.wpack + i));
+    if (tid == 0) s_flag = 0;
+
+    const int grp = tid / LPN, lig = tid % LPN;
+    const bool drop_in = p.training && net.drop[0] > 0.f;
+    const uint32_t key_in = dropout_key(p.seed, 0u, (uint32_t)p.t);
+    const float scale_in = drop_in ? 1.f / (1.f - net.drop[0]) : 1.f;
+    const int F_in = net.in_dim[0];
+
+    // BatchNormalization batch statistics of this CTA (training mode): columns 4*lig .. 4*lig+3
+    double bn_s1[4] = {0., 0., 0., 0.}, bn_s2[4] = {0., 0., 0., 0.};
+
+    const long long ntiles = (p.N + TN - 1) / TN;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long n0 = tile * TN;
+        const int nvalid = (int)min((long long)TN, p.N - n0);
+        __syncthreads();  // previous tile fully consumed (also orders the weight staging on the first pass)
+        for (int i = tid; i <= TN; i += NT) srow[i] = __ldg(p.rowptr + min(n0 + i, p.N));
+        __syncthreads();
+        const int ebase = srow[0];
+        const int ecount = srow[TN] - ebase;
+        const bool staged = ecount <= p.scol_cap;
+        if (staged) {
+            for (int i = tid; i < ecount; i += NT) {
+                scol[i] = __ldg(p.col + ebase + i);
+                if (HAS_VAL) sval[i] = __ldg(p.val + ebase + i);
+            }
+        }
+        __syncthreads();
+
+        // ---- 2. gather ------------------------------------------------------------------------------
+        for (int i = grp; i < TN; i += NGRP) {
+            float* rowA = bufA + i * SA;
+            if (i >= nvalid) {  // rows past the end: defined zeros
+                const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+                st4(rowA + 4 * lig, z);
+                st4(rowA + DP + 4 * lig, z);
+                for (int c = lig; c < CP / 4; c += LPN) st4(rowA + 2 * DP + 4 * c, z);
+                continue;
+            }
+            const long long n = n0 + i;
+            const int e0 = srow[i], e1 = srow[i + 1];
+            float4 agg = staged ? gather_rows<DP, HAS_VAL, true>(p.x_in, 4 * lig, e0 - ebase, e1 - ebase, scol, sval)
+                                : gather_rows<DP, HAS_VAL, false>(p.x_in, 4 * lig, e0, e1, p.col, p.val);
+            float4 own = ldg4(p.x_in + (size_t)n * DP + 4 * lig);
+            if (!HAS_VAL) {
+                const float s = __ldg(p.cst + (size_t)n * CP + net.C);
+                agg.x *= s; agg.y *= s; agg.z *= s; agg.w *= s;
+            }
+            if (p.agg_save) st4(p.agg_save + (size_t)n * DP + 4 * lig, agg);
+            if (drop_in) {
+                const uint64_t rbase = (uint64_t)n * (uint64_t)F_in;
+                float* o = reinterpret_cast<float*>(&own);
+                float* a = reinterpret_cast<float*>(&agg);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int j = 4 * lig + c;
+                    if (j < D) {
+                        o[c] = drop1(o[c], true, key_in, rbase + j, net.drop[0], scale_in);
+                        a[c] = drop1(a[c], true, key_in, rbase + D + net.NL_self + j, net.drop[0], scale_in);
+                    }
+                }
+            }
+            st4(rowA + 4 * lig, own);
+            st4(rowA + DP + 4 * lig, agg);
+            for (int c = lig; c < CP / 4; c += LPN) {
+                float4 v = ldg4(p.cst + (size_t)n * CP + 4 * c);
+                if (drop_in) {
+                    const uint64_t rbase = (uint64_t)n * (uint64_t)F_in;
+                    float* vv = reinterpret_cast<float*>(&v);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int kc = keras_input_col(2 * DP + 4 * c + q, D, DP, net.NL_self, net.NL_agg, net.AL);
+                        if (kc >= 0) vv[q] = drop1(vv[q], true, key_in, rbase + kc, net.drop[0], scale_in);
+                    }
+                }
+                st4(rowA + 2 * DP + 4 * c, v);
+            }
+        }
+        __syncthreads();
+
+        // ---- 3. MLP ---------------------------------------------------------------------------------
+        // hidden layers alternate bufB / bufA+DP; the last layer writes bufA + final_off.  When final_off == DP
+        // and the layer reads bufA, source and destination overlap: the layout guarantees one micro-tile per
+        // thread in that case, so the accumulators wait in registers across one barrier.
+        constexpr int NG = TN / 8;
+        for (int l = 0; l < net.L; ++l) {
+            const bool last = (l == net.L - 1);
+            const float* in = (l == 0) ? bufA : ((l & 1) ? bufB : bufA + DP);
+            const int in_stride = (l == 0 || !(l & 1)) ? SA : SB;
+            const float* W = sW + net.w_off[l];
+            const float* bias = sW + net.b_off[l];
+            const int HP = net.out_pad[l], act = net.act[l], odim = net.out_dim[l];
+            const float rate = net.drop[l + 1];
+            const bool drop_here = p.training && rate > 0.f;
+            const uint32_t key = dropout_key(p.seed, (uint32_t)(l + 1), (uint32_t)p.t);
+            const float dscale = drop_here ? 1.f / (1.f - rate) : 1.f;
+            float* out;
+            int out_stride;
+            if (last) { out = bufA + net.final_off; out_stride = SA; }
+            else if (l & 1) { out = bufA + DP; out_stride = SA; }
+            else { out = bufB; out_stride = SB; }
+            const bool hazard = last && !(l & 1) && net.final_off == DP;
+            const float* aff_a = sW + net.aff_off;
+            const float* aff_c = aff_a + HP;
+            const bool affine = last && !p.bn_train;
+
+            auto epi = [&](int ng, int cg, float (&acc)[8][4]) {
+                const float4 b4 = ld4(bias + 4 * cg);
+                const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int row = ng + NG * i;
+                    float v[4];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const int j = 4 * cg + c;
+                        float y = act_apply(act, acc[i][c] + bb[c]);
+                        if (drop_here) y = drop1(y, j < odim, key, (uint64_t)(n0 + row) * (uint64_t)odim + j, rate, dscale);
+                        if (affine) y = fmaf(aff_a[j], y, aff_c[j]);
+                        v[c] = (j < odim) ? y : 0.f;
+                    }
+                    st4(out + row * out_stride + 4 * cg, make_float4(v[0], v[1], v[2], v[3]));
+                }
+            };
+            if (hazard) {
+                const int CG = HP >> 2;
+                const int cg = tid % CG, ng = tid / CG;
+                const bool has_work = tid < NG * CG;  // NG*CG <= NT guaranteed by make_layout
+                float acc[8][4];
+                if (has_work) dense_micro<TN>(in + ng * in_stride, NG * in_stride, net.in_pad[l], W + 4 * cg, HP, acc);
+                __syncthreads();
+                if (has_work) epi(ng, cg, acc);
+            } else {
+                dense_tile<TN, NT>(in, in_stride, net.in_pad[l], W, HP, epi);
+            }
+            __syncthreads();
+        }
+
+        // ---- 4. epilogue: store + convergence test --------------------------------------------------
+        bool any_moving = false;
+        for (int item = tid; item < TN * LPN; item += NT) {
+            const int i = item / LPN;  // lig == item % LPN because NT % LPN == 0
+            const long long n = n0 + i;
+            const bool valid = i < nvalid;
+            float4 xn = ld4(bufA + i * SA + net.final_off + 4 * lig);
+            float d2 = 0.f, o2 = 0.f;
+            if (valid) {
+                st4(p.x_out + (size_t)n * DP + 4 * lig, xn);
+                if (p.bn_train) {
+                    bn_s1[0] += xn.x; bn_s1[1] += xn.y; bn_s1[2] += xn.z; bn_s1[3] += xn.w;
+                    bn_s2[0] += (double)xn.x * xn.x; bn_s2[1] += (double)xn.y * xn.y;
+                    bn_s2[2] += (double)xn.z * xn.z; bn_s2[3] += (double)xn.w * xn.w;
+                } else {
+                    const float4 xo = drop_in ? ldg4(p.x_in + (size_t)n * DP + 4 * lig) : ld4(bufA + i * SA + 4 * lig);
+                    const float dx = xn.x - xo.x, dy = xn.y - xo.y, dz = xn.z - xo.z, dw = xn.w - xo.w;
+                    d2 = dx * dx + dy * dy + dz * dz + dw * dw;
+                    o2 = xo.x * xo.x + xo.y * xo.y + xo.z * xo.z + xo.w * xo.w;
+                }
+            }
+            if (!p.bn_train) {
+#pragma unroll
+                for (int off = LPN / 2; off > 0; off >>= 1) {
+                    d2 += __shfl_xor_sync(0xffffffffu, d2, off);
+                    o2 += __shfl_xor_sync(0xffffffffu, o2, off);
+                }
+                any_moving |= valid && (sqrtf(d2) > p.thr * sqrtf(o2));
+            }
+        }
+        if (!p.bn_train && p.go_next) {
+            if (__any_sync(0xffffffffu, any_moving) && (tid & 31) == 0) s_flag = 1;
+        }
+    }
+
+    __syncthreads();
+    if (p.bn_train) {
+        // reduce the per-thread column sums: lanes sharing lig inside a warp, then warps through shared memory
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            for (int off = LPN; off < 32; off <<= 1) {
+                bn_s1[c] += __shfl_xor_sync(0xffffffffu, bn_s1[c], off);
+                bn_s2[c] += __shfl_xor_sync(0xffffffffu, bn_s2[c], off);
+            }
+        }
+        double* red = reinterpret_cast<double*>(bufA);  // [warps][LPN][8], fits (see net_layout.cuh)
+        const int warp = tid >> 5, lane = tid & 31;
+        if (lane < LPN) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                red[(warp * LPN + lane) * 8 + c] = bn_s1[c];
+                red[(warp * LPN + lane) * 8 + 4 + c] = bn_s2[c];
+            }
+        }
+        __syncthreads();
+        if (tid < LPN) {
+            double s1[4] = {0., 0., 0., 0.}, s2[4] = {0., 0., 0., 0.};
+            for (int w = 0; w < NT / 32; ++w)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) { s1[c] += red[(w * LPN + tid) * 8 + c]; s2[c] += red[(w * LPN + tid) * 8 + 4 + c]; }
+            double* dst = p.bn_partial + (size_t)blockIdx.x * 2 * DP;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) { dst[4 * tid + c] = s1[c]; dst[DP + 4 * tid + c] = s2[c]; }
+        }
+    } else {
+        if (tid == 0) {
+            if (p.go_next && s_flag) atomicOr(p.go_next, 1);
+            if (blockIdx.x == 0) *p.k_ptr = p.t + 1;
+        }
+    }
+}
+
+}  // namespace gnn

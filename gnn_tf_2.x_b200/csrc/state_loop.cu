@@ -1,0 +1,281 @@
+// state_loop.cu -- host side of the state-convergence loop: workspace carving, kernel selection, and the
+// enqueue of the whole while_loop (forward) / BPTT sweep (backward) without any host synchronisation.
+// C ABI: gnn_state_loop_workspace_bytes / gnn_state_loop_forward / gnn_state_loop_backward.
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+
+#include "state_kernels.h"
+
+namespace gnn {
+namespace {
+
+struct DeviceInfo {
+    int sms = 0, smem_optin = 0;
+};
+
+int device_info(DeviceInfo* out) {
+    static std::mutex mu;
+    static std::map<int, DeviceInfo> cache;
+    int dev = 0;
+    GNN_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find(dev);
+    if (it == cache.end()) {
+        DeviceInfo d;
+        GNN_CUDA(cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev));
+        GNN_CUDA(cudaDeviceGetAttribute(&d.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+        it = cache.emplace(dev, d).first;
+    }
+    *out = it->second;
+    return GNN_OK;
+}
+
+// resident CTAs per SM of a kernel at a dynamic shared-memory size (cached) + opt-in attribute
+int kernel_occupancy(const void* fn, int threads, size_t smem, int* ctas_per_sm) {
+    static std::mutex mu;
+    static std::map<std::pair<const void*, size_t>, int> cache;
+    std::lock_guard<std::mutex> lock(mu);
+    auto key = std::make_pair(fn, smem);
+    auto it = cache.find(key);
+    if (it == cache.end()) {
+        GNN_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int n = 0;
+        GNN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, threads, smem));
+        if (n < 1) GNN_FAIL(GNN_ERR_UNSUPPORTED, "kernel does not fit on an SM with %zu bytes of shared memory", smem);
+        it = cache.emplace(key, n).first;
+    } else {
+        // the attribute is per function: make sure the largest size seen so far stays configured
+        GNN_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    *ctas_per_sm = it->second;
+    return GNN_OK;
+}
+
+// ---- tile shapes --------------------------------------------------------------------------------------
+struct TileShape {
+    int tn, nt;
+};
+
+// big graphs: 128-node tiles; small graphs: 32-node tiles (one warp per CTA) so that more SMs get work
+TileShape pick_tile(long long N, int sms) {
+    const char* env = getenv("GNN_B200_TILE");
+    if (env) {
+        int v = atoi(env);
+        if (v == 128) return {128, 128};
+        if (v == 32) return {32, 32};
+    }
+    if ((N + 127) / 128 >= (long long)sms) return {128, 128};
+    return {32, 32};
+}
+
+// ---- workspace -----------------------------------------------------------------------------------------
+struct Workspace {
+    int* ctl;          // go[0..max_iter], k
+    float* wpack;
+    float* cst;
+    float* stats;      // [max_iter][4][DP] BatchNormalization batch statistics per iteration
+    double* bn_partial;
+    float* X;          // iterates: (max_iter + 1) slabs when saving, else 2 (ping-pong)
+    float* AGG;        // aggregated states per iteration (saved for backward)
+    float* H;          // pre-BatchNormalization outputs per iteration (training-mode BN)
+    float* G;          // backward: gradient wrt the current iterate
+    float* GS;         // backward: direct (own-state) part
+    float* GA;         // backward: part that flows through the aggregation
+    float* GH;         // backward: gradient wrt the pre-BN output (training-mode BN)
+    float* gcst;       // backward: gradient wrt the per-node constant row
+    float* gpartial;   // backward: per-CTA partial parameter gradients
+    double* bn_bwd_partial;
+    float* bn_bwd_sums;
+    double* bn_dgdb;   // [2][DP] dgamma | dbeta accumulated over the iterations
+    size_t slab;       // floats per [N, DP] slab
+    int x_slabs;
+    int max_ctas;
+    size_t total;
+};
+
+int carve(const gnn_graph* g, const gnn_loop_args* a, const NetLayout& lay, void* base, Workspace* w) {
+    DeviceInfo di;
+    GNN_TRY(device_info(&di));
+    const size_t N = (size_t)g->n_nodes;
+    const bool bn_train = a->training && lay.has_bn;
+    const bool save = a->save_for_backward != 0;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes ? bytes : 4, 256); return o; };
+    char* b = (char*)base;
+    memset(w, 0, sizeof(*w));
+    w->slab = N * (size_t)lay.DP;
+    w->max_ctas = di.sms * 32;
+    w->x_slabs = save ? a->max_iter + 1 : 2;
+    size_t o_ctl = take((size_t)(a->max_iter + 2) * sizeof(int));
+    size_t o_wp = take((size_t)lay.total_floats * 4);
+    size_t o_cst = take(N * (size_t)lay.CP * 4);
+    size_t o_stats = take(bn_train ? (size_t)a->max_iter * 4 * lay.DP * 4 : 0);
+    size_t o_part = take(bn_train ? (size_t)w->max_ctas * 2 * lay.DP * 8 : 0);
+    size_t o_X = take((size_t)w->x_slabs * w->slab * 4);
+    size_t o_AGG = take(save ? (size_t)a->max_iter * w->slab * 4 : 0);
+    size_t o_H = take(bn_train ? (size_t)(save ? a->max_iter : 1) * w->slab * 4 : 0);
+    size_t o_G = take(save ? w->slab * 4 : 0);
+    size_t o_GS = take(save ? w->slab * 4 : 0);
+    size_t o_GA = take(save ? w->slab * 4 : 0);
+    size_t o_GH = take(save && bn_train ? w->slab * 4 : 0);
+    size_t o_gcst = take(save ? N * (size_t)lay.CP * 4 : 0);
+    size_t o_gp = take(save ? (size_t)w->max_ctas * bwd_param_floats(lay) * 4 : 0);
+    size_t o_bp = take(save && bn_train ? (size_t)w->max_ctas * 2 * lay.DP * 8 : 0);
+    size_t o_bs = take(save && bn_train ? (size_t)2 * lay.DP * 4 : 0);
+    size_t o_dg = take(save && bn_train ? (size_t)2 * lay.DP * 8 : 0);
+    w->total = off;
+    if (b) {
+        w->ctl = (int*)(b + o_ctl); w->wpack = (float*)(b + o_wp); w->cst = (float*)(b + o_cst);
+        w->stats = (float*)(b + o_stats); w->bn_partial = (double*)(b + o_part); w->X = (float*)(b + o_X);
+        w->AGG = (float*)(b + o_AGG); w->H = (float*)(b + o_H); w->G = (float*)(b + o_G); w->GS = (float*)(b + o_GS);
+        w->GA = (float*)(b + o_GA); w->GH = (float*)(b + o_GH); w->gcst = (float*)(b + o_gcst);
+        w->gpartial = (float*)(b + o_gp); w->bn_bwd_partial = (double*)(b + o_bp); w->bn_bwd_sums = (float*)(b + o_bs);
+        w->bn_dgdb = (double*)(b + o_dg);
+    }
+    return GNN_OK;
+}
+
+int check_args(const gnn_graph* g, const gnn_mlp* net, const gnn_loop_args* a) {
+    if (!g || !net || !a) GNN_FAIL(GNN_ERR_INVALID, "NULL argument");
+    if (g->n_nodes < 0 || g->n_arcs < 0) GNN_FAIL(GNN_ERR_INVALID, "negative graph size");
+    if (a->max_iter < 0) GNN_FAIL(GNN_ERR_INVALID, "max_iter < 0");
+    if (g->n_nodes > 0 && (!g->rowptr || (!g->col && g->n_arcs > 0))) GNN_FAIL(GNN_ERR_INVALID, "graph CSR missing");
+    if (!g->val && !g->row_scale && g->n_arcs > 0) GNN_FAIL(GNN_ERR_INVALID, "graph needs val or row_scale");
+    if (a->NL_self < 0 || a->NL_agg < 0 || a->AL < 0) GNN_FAIL(GNN_ERR_INVALID, "negative label width");
+    for (int l = 0; l <= net->n_layers && l <= GNN_MAX_LAYERS; ++l)
+        if (net->drop_rate[l] > 0.f && a->training == 0) { /* inactive in inference */ }
+    return GNN_OK;
+}
+
+struct Plan {
+    NetLayout lay;
+    TileShape ts;
+    IterKernel kernel;
+    size_t smem;
+    int scol_cap;
+    int grid;
+    bool has_val;
+};
+
+int make_plan(const gnn_graph* g, const gnn_mlp* net, const gnn_loop_args* a, Plan* plan) {
+    DeviceInfo di;
+    GNN_TRY(device_info(&di));
+    plan->ts = pick_tile(g->n_nodes, di.sms);
+    GNN_TRY(make_layout(net, 1, a->D, a->NL_self, a->NL_agg, a->AL, plan->ts.tn, plan->ts.nt, &plan->lay));
+    const NetLayout& lay = plan->lay;
+    plan->has_val = g->val != nullptr && g->row_scale == nullptr;
+    const KernelSet* ks = kernel_set(lay.DP);
+    plan->kernel = ks ? ks->iter[plan->ts.tn == 128 ? 0 : 1][plan->has_val ? 1 : 0] : nullptr;
+    if (!plan->kernel) GNN_FAIL(GNN_ERR_UNSUPPORTED, "no kernel for padded state width %d", lay.DP);
+    const int TN = plan->ts.tn;
+    const size_t fixed = ((size_t)lay.fwd_floats + (size_t)TN * lay.SA + (size_t)TN * lay.SB + ((TN + 1 + 3) & ~3)) * 4;
+    // arc indices of a tile are staged in shared memory when they fit: ~1.6x the average tile
+    long long avg = g->n_nodes > 0 ? (g->n_arcs * TN) / g->n_nodes : 0;
+    int cap = (int)std::min<long long>(8192, std::max<long long>(256, (avg * 8 / 5 + 255) / 256 * 256));
+    const size_t per_arc = plan->has_val ? 8 : 4;
+    while (cap > 0 && fixed + cap * per_arc > (size_t)di.smem_optin) cap /= 2;
+    if (fixed > (size_t)di.smem_optin)
+        GNN_FAIL(GNN_ERR_UNSUPPORTED, "net_state too large for shared memory: %zu bytes needed, %d available", fixed, di.smem_optin);
+    plan->scol_cap = cap;
+    plan->smem = fixed + cap * per_arc;
+    int occ = 0;
+    GNN_TRY(kernel_occupancy((const void*)plan->kernel, plan->ts.nt, plan->smem, &occ));
+    long long ntiles = (g->n_nodes + TN - 1) / TN;
+    plan->grid = (int)std::max<long long>(1, std::min<long long>(ntiles, (long long)occ * di.sms));
+    if (plan->grid > di.sms * 32) plan->grid = di.sms * 32;
+    return GNN_OK;
+}
+
+}  // namespace
+}  // namespace gnn
+
+using namespace gnn;
+
+extern "C" int gnn_state_loop_workspace_bytes(const gnn_graph* g, const gnn_mlp* net, const gnn_loop_args* a, size_t* bytes) {
+    GNN_TRY(check_args(g, net, a));
+    if (!bytes) GNN_FAIL(GNN_ERR_INVALID, "NULL bytes");
+    NetLayout lay;
+    GNN_TRY(make_layout(net, 1, a->D, a->NL_self, a->NL_agg, a->AL, 128, 128, &lay));
+    Workspace w;
+    GNN_TRY(carve(g, a, lay, nullptr, &w));
+    *bytes = w.total;
+    return GNN_OK;
+}
+
+extern "C" int gnn_state_loop_forward(const gnn_graph* g, const gnn_mlp* net, const gnn_loop_args* a, void* workspace,
+                                      size_t workspace_bytes, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    GNN_TRY(check_args(g, net, a));
+    if (!a->x0 || !a->x_out) GNN_FAIL(GNN_ERR_INVALID, "x0 / x_out missing");
+    if (net->has_bn && (!net->bn_gamma || !net->bn_beta || !net->bn_moving_mean || !net->bn_moving_var))
+        GNN_FAIL(GNN_ERR_INVALID, "BatchNormalization parameters missing");
+    Plan plan;
+    GNN_TRY(make_plan(g, net, a, &plan));
+    const NetLayout& lay = plan.lay;
+    Workspace w;
+    GNN_TRY(carve(g, a, lay, workspace, &w));
+    if (!workspace || workspace_bytes < w.total) GNN_FAIL(GNN_ERR_WORKSPACE, "workspace %zu < %zu bytes", workspace_bytes, w.total);
+    const long long N = g->n_nodes;
+    const bool bn_train = a->training && lay.has_bn;
+    const bool save = a->save_for_backward != 0;
+    int* go = w.ctl;
+    int* kptr = w.ctl + a->max_iter + 1;
+
+    GNN_CUDA(cudaMemsetAsync(w.ctl, 0, (size_t)(a->max_iter + 2) * sizeof(int), stream));
+    {
+        PackParams pp;
+        pp.net = *net; pp.lay = lay; pp.wpack = w.wpack; pp.state_loop = 1;
+        pp.bn_inference = lay.has_bn && !a->training;
+        pack_net_kernel<<<(lay.total_floats + 255) / 256, 256, 0, stream>>>(pp);
+        GNN_LAUNCH_CHECK();
+    }
+    if (N == 0) {
+        GNN_CUDA(cudaMemsetAsync(a->k_out, 0, sizeof(float), stream));
+        return GNN_OK;
+    }
+    pack_cst_kernel<<<(unsigned)ceil_div(N * lay.CP, 256), 256, 0, stream>>>(a->nodes, a->agg_nodes, a->agg_arcs,
+                                                                             plan.has_val ? nullptr : g->row_scale, N, lay.NL_self,
+                                                                             lay.NL_agg, lay.AL, lay.CP, w.cst);
+    GNN_LAUNCH_CHECK();
+    init_state_kernel<<<(unsigned)ceil_div(N, 128), 128, 0, stream>>>(a->x0, N, lay.D, lay.DP, a->threshold, a->max_iter, w.X, go);
+    GNN_LAUNCH_CHECK();
+
+    IterParams p;
+    memset(&p, 0, sizeof(p));
+    p.rowptr = g->rowptr; p.col = g->col; p.val = plan.has_val ? g->val : nullptr; p.N = N;
+    p.cst = w.cst; p.wpack = w.wpack; p.k_ptr = kptr; p.thr = a->threshold; p.bn_partial = w.bn_partial;
+    p.bn_train = bn_train; p.seed = a->seed; p.training = a->training; p.scol_cap = plan.scol_cap; p.net = lay;
+    BnApplyKernel bn_apply = kernel_set(lay.DP)->bn_apply;
+
+    for (int t = 0; t < a->max_iter; ++t) {
+        const float* x_in = w.X + (size_t)(save ? t : (t & 1)) * w.slab;
+        float* x_next = w.X + (size_t)(save ? t + 1 : ((t + 1) & 1)) * w.slab;
+        p.x_in = x_in;
+        p.x_out = bn_train ? w.H + (size_t)(save ? t : 0) * w.slab : x_next;
+        p.agg_save = save ? w.AGG + (size_t)t * w.slab : nullptr;
+        p.go_cur = go + t;
+        p.go_next = (t + 1 < a->max_iter) ? go + t + 1 : nullptr;
+        p.t = t;
+        void* args[] = {(void*)&p};
+        GNN_CUDA(cudaLaunchKernel((const void*)plan.kernel, dim3(plan.grid), dim3(plan.ts.nt), args, plan.smem, stream));
+        GNN_LAUNCH_CHECK();
+        if (bn_train) {
+            float* stats = w.stats + (size_t)t * 4 * lay.DP;
+            bn_stats_kernel<<<(lay.DP + 31) / 32, 32, 0, stream>>>(go + t, w.bn_partial, plan.grid, lay.DP, lay.D, N, net->bn_gamma,
+                                                                  net->bn_beta, net->bn_moving_mean, net->bn_moving_var, net->bn_eps,
+                                                                  net->bn_momentum, stats);
+            GNN_LAUNCH_CHECK();
+            const long long items = N * (lay.DP / 4);
+            bn_apply<<<(unsigned)ceil_div(items, 256), 256, 0, stream>>>(go + t, p.go_next, kptr, t, p.x_out, x_in, stats, N, a->threshold, x_next);
+            GNN_LAUNCH_CHECK();
+        }
+    }
+    finalize_kernel<<<(unsigned)ceil_div(std::max<long long>(N * lay.D, 1), 256), 256, 0, stream>>>(
+        kptr, w.X, (long long)w.slab, save ? 0 : 2, N, lay.D, lay.DP, a->x_out, a->k_out);
+    GNN_LAUNCH_CHECK();
+    return GNN_OK;
+}
+
+#include "state_bwd_host.inl"

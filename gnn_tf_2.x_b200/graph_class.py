@@ -436,11 +436,39 @@ class GraphTensor:
     def has_nodegraph(self) -> bool:
         return self._ng_ids is not None or self._ng_dense is not None
 
+    # cached index tensors (boolean_mask without a device->host sync at every step) ------------------------------------
+    def _cached(self, name: str, build):
+        cache = self.__dict__.setdefault('_index_cache', dict())
+        key = (name, id(self.set_mask), id(self.output_mask))
+        if key not in cache: cache[key] = build()
+        return cache[key]
+
+    def mask_index(self):
+        """ int64 positions where set_mask & output_mask (GNN.py:275) """
+        import torch
+        return self._cached('mask', lambda: torch.nonzero(self.set_mask & self.output_mask, as_tuple=False)[:, 0])
+
+    def filtered_index(self):
+        """ positions, among the rows with output_mask, that also belong to set_mask (GNN_BaseClass.py:405-409) """
+        import torch
+        return self._cached('filtered', lambda: torch.nonzero(self.set_mask[self.output_mask], as_tuple=False)[:, 0])
+
+    def pool_nodes(self, out_nodes):
+        """ NodeGraph^T @ out_nodes (GNN.py:331-332) without the dense matrix: per-graph weighted segment sum """
+        import torch
+        if self._ng_dense is not None: return self._ng_dense.t() @ out_nodes
+        idx = self.mask_index()
+        ids = self._ng_ids.to(torch.int64).index_select(0, idx)
+        coeff = self._ng_coeff.index_select(0, idx)
+        pooled = torch.zeros((self._ng_cols, out_nodes.shape[1]), dtype=out_nodes.dtype, device=out_nodes.device)
+        return pooled.index_add(0, ids, coeff[:, None] * out_nodes)
+
     # -----------------------------------------------------------------------------------------------------------------
     def copy(self):
         """ shallow copy sharing the (immutable) device tensors, as the reference does (graph_class.py:347-351) """
         new = GraphTensor.__new__(GraphTensor)
         new.__dict__.update(self.__dict__)
+        new.__dict__['_index_cache'] = dict()
         return new
 
     # -----------------------------------------------------------------------------------------------------------------

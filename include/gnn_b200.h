@@ -1,0 +1,168 @@
+/*
+ * gnn_b200.h -- C ABI of the B200-native Scarselli-GNN state-convergence engine (libgnn_b200.so).
+ *
+ * The reference (sailab-code/GNN_tf_2.x) has no FFI: its boundary is the Python method
+ * GNNnodeBased.Loop(g, training) (GNN/GNN.py:251-280) and the third-party TensorFlow calls inside it.
+ * Each entry point below replaces one of those call sites; the citation says which.
+ *
+ * Conventions
+ *   - every pointer marked "device" is a CUDA device pointer owned by the CALLER (PyTorch); the library
+ *     borrows it for the duration of the call and allocates nothing persistent;
+ *   - `stream` is a cudaStream_t passed as void* (the caller's current stream); all work is enqueued on
+ *     it and the call returns without synchronising unless stated;
+ *   - return value: 0 on success, negative GNN_ERR_* otherwise; gnn_last_error() gives the message of
+ *     the last failure on the calling thread; nothing is thrown across the boundary;
+ *   - all floating point is fp32 (as the reference: graph_class.py:42-47), indices are int32 on the device.
+ *   - matrices are row-major, dense, with the leading dimension given where it can differ from the width.
+ */
+#ifndef GNN_B200_H
+#define GNN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GNN_B200_ABI_VERSION 1
+#define GNN_MAX_LAYERS 4 /* Dense layers per MLP */
+
+enum gnn_error {
+    GNN_OK = 0,
+    GNN_ERR_INVALID = -1,     /* bad argument */
+    GNN_ERR_UNSUPPORTED = -2, /* shape / option outside what the kernels implement */
+    GNN_ERR_WORKSPACE = -3,   /* workspace too small */
+    GNN_ERR_CUDA = -4         /* CUDA runtime error */
+};
+
+/* Keras activation strings accepted by MLP() (GNN/MLP.py:33) */
+enum gnn_activation {
+    GNN_ACT_LINEAR = 0, GNN_ACT_RELU = 1, GNN_ACT_TANH = 2, GNN_ACT_SIGMOID = 3,
+    GNN_ACT_SELU = 4, GNN_ACT_ELU = 5, GNN_ACT_SOFTMAX = 6, GNN_ACT_SOFTPLUS = 7
+};
+
+const char* gnn_last_error(void);
+int gnn_abi_version(void);
+/* number of SMs and opt-in shared memory per block of the current device */
+int gnn_device_info(int32_t* sm_count, int32_t* smem_optin_bytes, int32_t* cc_major, int32_t* cc_minor);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Arc preprocessing.  Replaces GraphTensor.COO2SparseTransposedTensor (GNN/graph_class.py:364-372: python
+ * list(zip(col,row)) -> tf.SparseTensor -> tf.sparse.reorder) and, for the backward pass, what TF derives
+ * internally for the gradient of sparse_dense_matmul (A^T g).
+ *
+ * Input: COO entries (row[i], col[i], val[i]) of the ALREADY TRANSPOSED matrix (row = destination node).
+ * Output: CSR in row-major order (entries sorted by (row, col), ties in input order = stable):
+ *   rowptr[n_rows+1], col_sorted[nnz], val_sorted[nnz], perm[nnz] (input position of each stored entry),
+ *   row_scale[n_rows] = value of the first entry of each row (0 for empty rows), *rows_uniform = 1 when every
+ *   row holds one repeated value (true for 'sum' / 'average' / 'normalized' aggregation).
+ * Optional transposed structure (pass NULL rowptr_T to skip): entries sorted by (col, CSR position):
+ *   rowptr_T[n_cols+1], col_T[nnz] (= row of the entry), perm_T[nnz] (= CSR position), val_T[nnz].
+ * Call with workspace == NULL to get the required size in *workspace_bytes.
+ * Synchronises the stream once (to report rows_uniform to the host).
+ */
+int gnn_csr_build(const int32_t* row, const int32_t* col, const float* val, /* device [nnz] */
+                  int64_t nnz, int64_t n_rows, int64_t n_cols,
+                  int32_t* rowptr, int32_t* col_sorted, float* val_sorted, int32_t* perm, float* row_scale,
+                  int32_t* rowptr_T, int32_t* col_T, int32_t* perm_T, float* val_T,
+                  int32_t* rows_uniform, /* host out */
+                  void* workspace, size_t* workspace_bytes, void* stream);
+
+/* Sparse x dense, out[r, 0:F] = sum_e val[e] * dense[col[e], 0:F] over the stored entries of row r in stored
+ * order (deterministic, no atomics).  Replaces tf.sparse.sparse_dense_matmul at GNN/GNN.py:259 (ArcNode^T x arc
+ * labels) and :263 (Adjacency^T x node labels); with the transposed structure it is also their gradient.
+ * val may be NULL (all ones).  accumulate != 0 adds to `out` instead of overwriting it. */
+int gnn_spmm(const int32_t* rowptr, const int32_t* col, const float* val, int64_t n_rows,
+             const float* dense, int64_t ld_dense, int32_t F, float* out, int64_t ld_out, int32_t accumulate,
+             void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * MLP description: what GNN/MLP.py:11-64 builds -- Dense chain, Dropout in front of Dense l (drop_rate[l]) or
+ * behind the last Dense (drop_rate[n_layers]), optional trailing BatchNormalization (Keras defaults).
+ */
+typedef struct gnn_mlp {
+    int32_t n_layers;                    /* 1..GNN_MAX_LAYERS */
+    int32_t dims[GNN_MAX_LAYERS + 1];    /* dims[0] = input width, dims[l+1] = units of Dense l */
+    int32_t act[GNN_MAX_LAYERS];         /* gnn_activation */
+    const float* W[GNN_MAX_LAYERS];      /* device, Keras kernel layout [dims[l], dims[l+1]] */
+    const float* b[GNN_MAX_LAYERS];      /* device [dims[l+1]] */
+    float drop_rate[GNN_MAX_LAYERS + 1]; /* 0 = no dropout at that position */
+    int32_t has_bn;
+    const float* bn_gamma;               /* device [dims[n_layers]] */
+    const float* bn_beta;
+    float* bn_moving_mean;               /* device; updated in place once per loop iteration when training */
+    float* bn_moving_var;
+    float bn_eps;
+    float bn_momentum;
+} gnn_mlp;
+
+/* gradients of the trainable variables, Keras layouts; every non-NULL buffer is OVERWRITTEN */
+typedef struct gnn_mlp_grad {
+    float* dW[GNN_MAX_LAYERS];
+    float* db[GNN_MAX_LAYERS];
+    float* dgamma;
+    float* dbeta;
+} gnn_mlp_grad;
+
+/* destination-sorted CSR of Adjacency^T (+ its transpose), as produced by gnn_csr_build */
+typedef struct gnn_graph {
+    int64_t n_nodes;
+    int64_t n_arcs;
+    const int32_t* rowptr;    /* [n_nodes+1] */
+    const int32_t* col;       /* [n_arcs] source node of every stored arc */
+    const float* val;         /* [n_arcs] per-arc weight; NULL => use row_scale */
+    const float* row_scale;   /* [n_nodes] common weight of the arcs entering a node; NULL => use val */
+    const int32_t* rowptr_T;  /* [n_nodes+1] (backward only) */
+    const int32_t* col_T;     /* [n_arcs] destination node, source-sorted */
+    const float* val_T;       /* [n_arcs] weights in transposed order; NULL with row_scale */
+} gnn_graph;
+
+/* ------------------------------------------------------------------------------------------------------------
+ * The state-convergence loop.  Replaces tf.while_loop(self.condition, self.convergence, ...) at
+ * GNN/GNN.py:271-272 together with condition (:202-220) and convergence (:223-242), and -- for
+ * gnn_state_loop_backward -- what tf.GradientTape replays for it (GNN/GNN_BaseClass.py:233-237).
+ *
+ * net_state input columns, in the reference's order (GNN.py:228-237):
+ *   [ state(D) | nodes(NL_self) | agg_state(D) | agg_nodes(NL_agg) | agg_arcs(AL) ],  D = state width
+ *   (NL_self = NL_agg = NL when state_vect_dim > 0, else 0).
+ * One iteration: agg_state = Adjacency^T x state (segment sum over incoming arcs, stored order),
+ * state_new = net_state(input).  Iterations run while any node has
+ * ||state - state_old||_2 > threshold * ||state_old||_2 and k < max_iter; state_old starts as ones (:266).
+ * The whole loop is enqueued without host synchronisation; *k_out (device float) is the iteration count.
+ */
+typedef struct gnn_loop_args {
+    int32_t D, NL_self, NL_agg, AL;
+    const float* x0;          /* device [N, D] */
+    const float* nodes;       /* device [N, NL_self] (unused when NL_self == 0) */
+    const float* agg_nodes;   /* device [N, NL_agg] */
+    const float* agg_arcs;    /* device [N, AL] */
+    int32_t max_iter;
+    float threshold;
+    int32_t training;         /* Keras `training` flag: dropout active, BatchNormalization uses batch statistics */
+    int32_t save_for_backward;/* keep the iterates in the workspace so that gnn_state_loop_backward can run */
+    uint32_t seed;            /* dropout generator seed of this call */
+    float* x_out;             /* device [N, D] converged state */
+    float* k_out;             /* device [1] number of iterations, float32 as GNN.py:267 */
+} gnn_loop_args;
+
+int gnn_state_loop_workspace_bytes(const gnn_graph* g, const gnn_mlp* net, const gnn_loop_args* a, size_t* bytes);
+
+int gnn_state_loop_forward(const gnn_graph* g, const gnn_mlp* net, const gnn_loop_args* a,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
+/* BPTT through the iterations saved by the matching forward call (same g/net/a/workspace).
+ * g_x: device [N, D] gradient of the loss wrt the converged state (x_out).
+ * Outputs (NULL to skip): grad of the net_state variables, g_x0 [N, D], g_nodes [N, NL_self],
+ * g_agg_nodes [N, NL_agg], g_agg_arcs [N, AL] (the last three are needed only by LGNN: LGNN.py:258-259). */
+int gnn_state_loop_backward(const gnn_graph* g, const gnn_mlp* net, const gnn_loop_args* a, const float* g_x,
+                            gnn_mlp_grad* grad, float* g_x0, float* g_nodes, float* g_agg_nodes, float* g_agg_arcs,
+                            void* workspace, size_t workspace_bytes, void* stream);
+
+/* number of kernels the library has launched since the last reset (for bench.py's gpu_launches) */
+int64_t gnn_launch_count(int32_t reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GNN_B200_H */

@@ -34,24 +34,32 @@ _M32 = 0xFFFFFFFF
 # dropout generator (independent restatement of the product's counter-based generator; tests check they agree)
 # =====================================================================================================================
 def _fmix32(x):
-    x = x & _M32
-    x = x ^ (x >> 16)
-    x = (x * 0x85EBCA6B) & _M32
-    x = x ^ (x >> 13)
-    x = (x * 0xC2B2AE35) & _M32
-    return x ^ (x >> 16)
+    """ murmur3 finaliser on uint32 values held in uint64 arrays (products stay below 2**64) """
+    x = x.astype(np.uint64) & np.uint64(_M32)
+    x = x ^ (x >> np.uint64(16))
+    x = (x * np.uint64(0x85EBCA6B)) & np.uint64(_M32)
+    x = x ^ (x >> np.uint64(13))
+    x = (x * np.uint64(0xC2B2AE35)) & np.uint64(_M32)
+    return x ^ (x >> np.uint64(16))
 
 
 def keep_mask(seed: int, stream: int, step: int, rows: int, cols: int, rate: float) -> np.ndarray:
     """ keep[n, j] = u >= rate, u = (h >> 8) / 2**24, h = fmix32(fmix32(lo ^ key) + hi*0xC2B2AE35 + 0x165667B1),
     idx = n*cols + j, key = fmix32(fmix32(seed + 0x9E3779B9*(stream+1)) ^ (step*0x85EBCA6B + 0x27D4EB2F)) """
-    key = int(_fmix32(np.int64(_fmix32(np.int64((seed + 0x9E3779B9 * (stream + 1)) & _M32))) ^
-                      np.int64((step * 0x85EBCA6B + 0x27D4EB2F) & _M32)))
+    def fmix_int(x: int) -> int:
+        x &= _M32
+        x ^= x >> 16
+        x = (x * 0x85EBCA6B) & _M32
+        x ^= x >> 13
+        x = (x * 0xC2B2AE35) & _M32
+        return x ^ (x >> 16)
+
+    key = fmix_int(fmix_int(seed + 0x9E3779B9 * (stream + 1)) ^ ((step * 0x85EBCA6B + 0x27D4EB2F) & _M32))
     idx = np.arange(rows, dtype=np.int64)[:, None] * cols + np.arange(cols, dtype=np.int64)[None, :]
-    lo, hi = idx & _M32, (idx >> 32) & _M32
-    v = _fmix32(lo ^ key)
-    v = _fmix32((v + hi * 0xC2B2AE35 + 0x165667B1) & _M32)
-    return ((v >> 8).astype(np.float32) * np.float32(1.0 / 16777216.0)) >= np.float32(rate)
+    lo, hi = (idx & _M32).astype(np.uint64), ((idx >> 32) & _M32).astype(np.uint64)
+    v = _fmix32(lo ^ np.uint64(key))
+    v = _fmix32((v + hi * np.uint64(0xC2B2AE35) + np.uint64(0x165667B1)) & np.uint64(_M32))
+    return ((v >> np.uint64(8)).astype(np.float32) * np.float32(1.0 / 16777216.0)) >= np.float32(rate)
 
 
 # =====================================================================================================================

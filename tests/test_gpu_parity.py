@@ -1,0 +1,235 @@
+"""GPU parity tests proper (run on the B200 box with -m gpu): the CUDA product path, called through the C ABI, against
+the CPU oracle on identical seeded inputs.  CSR / index construction and iteration counts exact; states, outputs, loss and
+gradients within 1e-4 relative (fp32)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from tests.parity import random_case, run_cuda, run_oracle, assert_parity, build_product, rel_err, TOL
+
+pytestmark = pytest.mark.gpu
+
+
+def _require_gpu():
+    if not torch.cuda.is_available(): pytest.fail('GPU test selected but no CUDA device is visible')
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# arc preprocessing
+# ---------------------------------------------------------------------------------------------------------------------
+def _check_csr(coo, with_transpose):
+    from gnn_b200 import _native
+    from oracle import graph_oracle as GO
+    sp = _native.csr_from_coo_transposed(coo, with_transpose=with_transpose)
+    want = GO.transposed_row_major(coo.row, coo.col, coo.data, coo.shape)
+    np.testing.assert_array_equal(sp.rowptr.cpu().numpy(), want['rowptr'])
+    np.testing.assert_array_equal(sp.col.cpu().numpy(), want['indices'][:, 1])
+    np.testing.assert_array_equal(sp.values.cpu().numpy(), want['values'])
+    np.testing.assert_array_equal(sp.perm.cpu().numpy(), want['perm'])
+    np.testing.assert_array_equal(sp.indices.cpu().numpy(), want['indices'])
+    assert sp.dense_shape == tuple(want['dense_shape'])
+    if with_transpose:
+        rowptr_T, col_T, perm_T = GO.csr_transpose(want['rowptr'], want['indices'][:, 1], coo.shape[0])
+        np.testing.assert_array_equal(sp.rowptr_T.cpu().numpy(), rowptr_T)
+        np.testing.assert_array_equal(sp.col_T.cpu().numpy(), col_T)
+        np.testing.assert_array_equal(sp.perm_T.cpu().numpy(), perm_T)
+        np.testing.assert_array_equal(sp.values_T.cpu().numpy(), want['values'][perm_T])
+    return sp
+
+
+@pytest.mark.parametrize('mode', ['average', 'normalized', 'sum'])
+def test_csr_simple_graph_known_answer(mode):
+    _require_gpu()
+    from gnn_b200 import GNN_utils as utils
+    g = utils.simple_graph('n', mode)
+    sp = _check_csr(g.Adjacency, True)
+    np.testing.assert_array_equal(sp.rowptr.cpu().numpy(), [0, 2, 4, 7, 8])
+    np.testing.assert_array_equal(sp.col.cpu().numpy(), [1, 2, 0, 2, 0, 1, 3, 2])
+    assert sp.row_scale is not None
+    _check_csr(g.ArcNode, False)
+
+
+def test_csr_golden_merge(golden_dir):
+    _require_gpu()
+    from scipy.sparse import coo_matrix
+    ref = dict(np.load(f'{golden_dir}/graphobject_merge_n.npz'))
+    adj = coo_matrix((ref['adj_data'], (ref['adj_row'], ref['adj_col'])), shape=tuple(ref['adj_shape']))
+    sp = _check_csr(adj, True)
+    from gnn_b200 import _native
+    got = _native.spmm(sp.rowptr, sp.col, sp.values, torch.as_tensor(ref['nodes'], device='cuda'))
+    np.testing.assert_allclose(got.cpu().numpy(), ref['adjT_nodes'], rtol=1e-6, atol=1e-6)
+    an = coo_matrix((ref['arcnode_data'], (ref['arcnode_row'], ref['arcnode_col'])), shape=tuple(ref['arcnode_shape']))
+    sp2 = _check_csr(an, False)
+    got = _native.spmm(sp2.rowptr, sp2.col, sp2.values, torch.as_tensor(ref['arcs'][:, 2:].copy(), device='cuda'))
+    np.testing.assert_allclose(got.cpu().numpy(), ref['arcnodeT_labels'], rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize('n,e,seed', [(1, 0, 0), (5, 0, 1), (7, 3, 2), (1000, 20000, 3), (50000, 400000, 4)])
+def test_csr_random(n, e, seed):
+    _require_gpu()
+    from scipy.sparse import coo_matrix
+    rng = np.random.default_rng(seed)
+    row, col = rng.integers(0, n, e), rng.integers(0, max(n // 2, 1), e)   # upper half of the nodes gets no arc (empty rows)
+    if e > 3: row[2], col[2] = row[0], col[0]                              # duplicate entries
+    data = rng.random(e).astype(np.float32)
+    sp = _check_csr(coo_matrix((data, (row, col)), shape=(n, n)), True)
+    assert sp.row_scale is None or e < 2
+
+
+def test_row_scale_detection():
+    _require_gpu()
+    from gnn_b200.graph_class import GraphObject, GraphTensor
+    c = random_case(seed=5, n_nodes=300, n_arcs=2000)
+    for mode in ('average', 'normalized', 'sum'):
+        g = GraphObject(c['arcs'], c['nodes'], c['targets'], set_mask=c['set_mask'], output_mask=c['output_mask'], aggregation_mode=mode)
+        gt = GraphTensor.fromGraphObject(g)
+        assert gt.Adjacency.row_scale is not None and gt.ArcNode.row_scale is not None
+        indeg = np.bincount(c['arcs'][:, 1].astype(int), minlength=300)
+        want = {'sum': np.where(indeg > 0, 1.0, 0.0), 'normalized': np.where(indeg > 0, 1 / 2000, 0.0),
+                'average': np.where(indeg > 0, 1 / np.maximum(indeg, 1), 0.0)}[mode]
+        np.testing.assert_allclose(gt.Adjacency.row_scale.cpu().numpy(), want.astype(np.float32), rtol=1e-7)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# forward (inference) parity
+# ---------------------------------------------------------------------------------------------------------------------
+FWD_CASES = {
+    'ds0_nl3': dict(NL=3, AL=1, DS=0, act='tanh', max_iter=5),
+    'ds0_nl14_mutag': dict(NL=14, AL=3, DS=0, act='selu', max_iter=5, n_nodes=970, n_arcs=1970),
+    'ds0_nl5': dict(NL=5, AL=1, DS=0, act='sigmoid', max_iter=8),
+    'ds8': dict(NL=3, AL=2, DS=8, act='tanh', max_iter=30, threshold=0.001),
+    'ds32_c4like': dict(NL=3, AL=1, DS=32, act='selu', max_iter=50, threshold=0.0, n_nodes=700, n_arcs=7000, bn=True),
+    'ds20_pad32': dict(NL=2, AL=2, DS=20, act='relu', max_iter=10),
+    'ds64': dict(NL=3, AL=1, DS=64, act='tanh', max_iter=6),
+    'ds100_pad128': dict(NL=1, AL=1, DS=100, act='tanh', max_iter=4, n_nodes=150, n_arcs=900),
+    'hidden2': dict(NL=3, AL=2, DS=6, hidden=(10,), act='tanh', max_iter=12),
+    'hidden3_elu': dict(NL=4, AL=1, DS=0, hidden=(9, 7), act='elu', max_iter=10),
+    'hidden4': dict(NL=2, AL=1, DS=5, hidden=(8, 12, 6), act='softplus', max_iter=7),
+    'sum_mode': dict(NL=3, AL=1, DS=4, act='tanh', aggregation='sum', max_iter=10, weight_scale=0.05),
+    'normalized_mode': dict(NL=3, AL=1, DS=4, act='tanh', aggregation='normalized', max_iter=10),
+    'custom_arcnode': dict(NL=3, AL=2, DS=8, act='tanh', custom_arcnode=True, max_iter=10),
+    'bn_inference': dict(NL=3, AL=1, DS=0, act='selu', bn=True, max_iter=5),
+    'linear_converges': dict(NL=3, AL=1, DS=3, act='linear', max_iter=60, threshold=0.01, weight_scale=0.05),
+    'max_iter0': dict(NL=3, AL=1, DS=2, act='tanh', max_iter=0),
+    'tiny': dict(NL=2, AL=1, DS=0, act='tanh', n_nodes=3, n_arcs=4, max_iter=5, isolated=False, duplicates=False, masks=False),
+    'no_arcs': dict(NL=2, AL=1, DS=3, act='tanh', n_nodes=40, n_arcs=0, max_iter=5, duplicates=False),
+}
+
+
+@pytest.mark.parametrize('name', sorted(FWD_CASES))
+def test_forward_parity(name):
+    _require_gpu()
+    case = random_case(seed=sorted(FWD_CASES).index(name), **FWD_CASES[name])
+    got, want = run_cuda(case, training=False), run_oracle(case, training=False)
+    assert_parity(got, want)
+
+
+@pytest.mark.parametrize('tile', ['128', '32'])
+def test_forward_parity_both_tile_shapes(tile, monkeypatch):
+    _require_gpu()
+    monkeypatch.setenv('GNN_B200_TILE', tile)
+    case = random_case(seed=77, n_nodes=1111, n_arcs=9000, NL=3, AL=1, DS=32, act='selu', max_iter=9, threshold=0.0, bn=True)
+    assert_parity(run_cuda(case, training=False), run_oracle(case, training=False))
+    case = random_case(seed=78, n_nodes=777, n_arcs=5000, NL=14, AL=3, DS=0, act='selu', max_iter=5)
+    assert_parity(run_cuda(case, training=False), run_oracle(case, training=False))
+
+
+def test_forward_large_tiles_and_determinism():
+    """ 40k nodes -> 128-node tiles on every SM; two runs must agree bit for bit (no atomics in the data path) """
+    _require_gpu()
+    case = random_case(seed=9, n_nodes=40000, n_arcs=400000, NL=3, AL=1, DS=32, act='selu', max_iter=6, threshold=0.0, bn=True)
+    a = run_cuda(case, training=False)
+    b = run_cuda(case, training=False)
+    assert a['k'] == b['k'] == 6
+    np.testing.assert_array_equal(a['state'], b['state'])
+    assert_parity(a, run_oracle(case, training=False))
+
+
+def test_graph_and_edge_based_forward():
+    _require_gpu()
+    case = random_case(seed=21, n_nodes=400, n_arcs=1600, NL=4, AL=2, DS=0, act='tanh', problem='g', n_graphs=13, max_iter=5)
+    assert_parity(run_cuda(case, training=False), run_oracle(case, training=False))
+    case = random_case(seed=22, n_nodes=120, n_arcs=700, NL=3, AL=2, DS=4, act='tanh', problem='a', max_iter=6)
+    assert_parity(run_cuda(case, training=False), run_oracle(case, training=False))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# training: BPTT gradients
+# ---------------------------------------------------------------------------------------------------------------------
+TRAIN_CASES = {
+    'ds0_tanh': dict(NL=3, AL=1, DS=0, act='tanh', max_iter=5),
+    'ds0_selu_mutag': dict(NL=14, AL=3, DS=0, act='selu', max_iter=5, n_nodes=600, n_arcs=1300, problem='g', n_graphs=20),
+    'ds8_tanh': dict(NL=3, AL=2, DS=8, act='tanh', max_iter=12, threshold=0.01),
+    'ds32_selu': dict(NL=3, AL=1, DS=32, act='selu', max_iter=10, threshold=0.0, n_nodes=500, n_arcs=5000),
+    'custom_arcnode': dict(NL=3, AL=2, DS=8, act='sigmoid', custom_arcnode=True, max_iter=8),
+    'sum_mode': dict(NL=2, AL=1, DS=4, act='tanh', aggregation='sum', max_iter=6, weight_scale=0.05),
+    'hidden2': dict(NL=3, AL=2, DS=6, hidden=(10,), act='tanh', max_iter=8),
+    'hidden3': dict(NL=4, AL=1, DS=0, hidden=(9, 7), act='elu', max_iter=6),
+    'dropout_in': dict(NL=3, AL=1, DS=0, act='selu', max_iter=5, drop=[0.1, 0.0]),
+    'dropout_everywhere': dict(NL=3, AL=2, DS=6, hidden=(10,), act='tanh', max_iter=6, drop=[0.2, 0.3, 0.1], out_drop=[0.1, 0.0]),
+    'bn_train': dict(NL=3, AL=1, DS=0, act='selu', bn=True, max_iter=5),
+    'bn_train_ds16': dict(NL=3, AL=1, DS=16, act='tanh', bn=True, max_iter=7, threshold=0.0, n_nodes=900, n_arcs=6000),
+    'starter_default': dict(NL=3, AL=1, DS=0, act='selu', bn=True, out_bn=True, drop=[0.1, 0.0], out_drop=[0.1, 0.0], max_iter=5,
+                            n_nodes=900, n_arcs=7000),
+    'edge_based': dict(NL=3, AL=2, DS=4, act='tanh', problem='a', max_iter=5, n_nodes=100, n_arcs=600),
+    'k_zero': dict(NL=3, AL=1, DS=2, act='tanh', max_iter=0),
+}
+
+
+@pytest.mark.parametrize('name', sorted(TRAIN_CASES))
+def test_training_parity(name):
+    _require_gpu()
+    case = random_case(seed=100 + sorted(TRAIN_CASES).index(name), **TRAIN_CASES[name])
+    mean = name != 'k_zero'    # gradients / k with k == 0 are not finite in the reference either
+    got, want = run_cuda(case, training=True, mean=mean), run_oracle(case, training=True, mean=mean)
+    assert_parity(got, want)
+
+
+@pytest.mark.parametrize('tile', ['128', '32'])
+def test_training_parity_tile_shapes(tile, monkeypatch):
+    _require_gpu()
+    monkeypatch.setenv('GNN_B200_TILE', tile)
+    case = random_case(seed=300, n_nodes=10000, n_arcs=60000, NL=3, AL=1, DS=32, act='selu', bn=True, max_iter=4, threshold=0.0)
+    assert_parity(run_cuda(case, training=True), run_oracle(case, training=True))
+
+
+def test_backward_is_deterministic():
+    _require_gpu()
+    case = random_case(seed=301, n_nodes=5000, n_arcs=40000, NL=3, AL=1, DS=8, act='tanh', max_iter=5)
+    a, b = run_cuda(case, training=True), run_cuda(case, training=True)
+    for x, y in zip(a['gs'] + a['go'], b['gs'] + b['go']): np.testing.assert_array_equal(x, y)
+
+
+def test_label_gradients_for_lgnn():
+    """ gradients wrt node labels / aggregated labels / x0 (needed by LGNN parallel & residual modes) """
+    _require_gpu()
+    from gnn_b200.state_loop import state_loop, sparse_dense
+    from oracle import gnn_oracle as O
+    case = random_case(seed=400, n_nodes=150, n_arcs=900, NL=3, AL=2, DS=5, act='tanh', max_iter=6, masks=False)
+    g, gt, gnn = build_product(case)
+    nodes = gt.nodes.clone().requires_grad_()
+    labels = gt.arcs[:, 2:].clone().requires_grad_()
+    x0 = torch.as_tensor(case['x0'], device='cuda').requires_grad_()
+    agg_arcs = sparse_dense(gt.ArcNode, labels)
+    agg_nodes = sparse_dense(gt.Adjacency, nodes)
+    k, x = state_loop(gt.Adjacency, gnn.net_state, x0, nodes, agg_nodes, agg_arcs, max_iteration=6, threshold=0.01, training=True)
+    probe = torch.as_tensor(np.random.default_rng(0).standard_normal(tuple(x.shape)).astype(np.float32), device='cuda')
+    g_nodes, g_labels, g_x0 = torch.autograd.grad((x * probe).sum(), [nodes, labels, x0])
+    # oracle
+    og = O.OracleGraph.build(case['arcs'], case['nodes'], case['targets'], 'n', None, None, 1, None, 'average')
+    on = og.nodes.clone().requires_grad_()
+    ol = og.arcs[:, 2:].clone().requires_grad_()
+    ox0 = torch.tensor(case['x0']).requires_grad_()
+    net_s = O.OracleMLP.from_weights(case['ws'], case['acts_state'])
+    state, state_old, kk = ox0, torch.ones_like(ox0), 0.0
+    aa, an = O.spmm(og.arcnode, ol), O.spmm(og.adj, on)
+    while O.condition(kk, state.detach(), state_old.detach(), float(np.float32(0.01)), 6):
+        inp = torch.cat([state, on, O.spmm(og.adj, state), an, aa], dim=1)
+        state, state_old, kk = net_s(inp, True), state, kk + 1
+    w_nodes, w_labels, w_x0 = torch.autograd.grad((state * probe.cpu()).sum(), [on, ol, ox0])
+    assert float(k) == kk
+    assert rel_err(g_nodes.cpu().numpy(), w_nodes.numpy()) < TOL
+    assert rel_err(g_labels.cpu().numpy(), w_labels.numpy()) < TOL
+    assert rel_err(g_x0.cpu().numpy(), w_x0.numpy()) < TOL
