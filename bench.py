@@ -1,0 +1,319 @@
+#!/usr/bin/env python
+"""bench.py -- the state-convergence loop on BASELINE.json's headline workload (C4: one synthetic graph, 1M nodes /
+10M arcs, node classification, state_dim 32, max_iteration 50), metric arc-updates/sec = arcs x iterations / time.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload c4u|c4l] [--nodes N --arcs E]
+
+One JSON line on stdout (rank 0).  Keys beyond the base contract:
+  value        forward Loop (training=False, threshold 0 so that k = max_iteration), inputs resident in HBM
+  e2e          same metric through the public call gnn(GraphObject) with HOST buffers: host->device copy of the graph
+               arrays (pinned), CSR build, loop, device->host read of the outputs, every step
+  train        forward + BPTT backward + optimizer (BaseClass.training_step) arc-updates/sec and epoch time
+  roofline     fused iteration kernel: algorithmic bytes per launch / mean launch time (CUDA events on the launching
+               stream inside libgnn_b200.so) against MEASURED_PEAKS.json
+  cpu_baseline the oracle port (torch-CPU restatement of the reference's TF path, NOT TensorFlow) on the host cores,
+               bounded sample of the same workload
+`--impl reference` times that CPU port alone (the reference's TensorFlow cannot be installed: see DESIGN.md).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path: sys.path.insert(0, ROOT)
+
+# algorithmic bytes per arc-update of the fused forward iteration (SURVEY.md 8d / DESIGN.md): every array touched
+# once, gathered state re-used from L2:  4 E (source index) + N (4 rowptr + 4 D read + 4 D write + 4 (2 NL + AL))
+def algorithmic_bytes_per_iteration(N, E, D, NL, AL, per_arc_weights=False):
+    return 4 * E * (2 if per_arc_weights else 1) + N * (4 + 8 * D + 4 * (2 * NL + AL))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# workload
+# ---------------------------------------------------------------------------------------------------------------------
+def make_workload(name: str, N: int, E: int, seed: int = 0):
+    """ in-degree exactly E/N per node; sources uniform ('c4u') or within +-2048 of the destination
+    ('c4l'); NL=3, AL=1, T=2, labels U(-1,1); x0 = 0.1 randn; net_state Dense(71->32, selu)+BN, randn*sqrt(1/71) """
+    rng = np.random.default_rng(seed)
+    deg = E // N
+    dst = np.repeat(np.arange(N, dtype=np.int64), deg)
+    if name == 'c4l':
+        delta = rng.integers(1, 2049, dst.shape[0]) * rng.choice([-1, 1], dst.shape[0])
+        src = (dst + delta) % N
+    else:
+        src = rng.integers(0, N, dst.shape[0])
+    NL, AL, T, DS = 3, 1, 2, 32
+    arcs = np.empty((dst.shape[0], 2 + AL), dtype=np.float32)
+    arcs[:, 0], arcs[:, 1] = src, dst
+    arcs[:, 2:] = rng.uniform(-1, 1, (dst.shape[0], AL))
+    nodes = rng.uniform(-1, 1, (N, NL)).astype(np.float32)
+    targets = np.eye(T, dtype=np.float32)[np.argmax(nodes[:, :2], axis=1)]
+    x0 = (0.1 * rng.standard_normal((N, DS))).astype(np.float32)
+    F = AL + 2 * (NL + DS)
+    ws = [(rng.standard_normal((F, DS)) * np.sqrt(1.0 / F)).astype(np.float32), np.zeros(DS, np.float32),
+          np.ones(DS, np.float32), np.zeros(DS, np.float32), np.zeros(DS, np.float32), np.ones(DS, np.float32)]
+    Fo = NL + DS
+    # output net: Dense(softmax) only. The reference default appends BatchNormalization after the softmax; with T = 2
+    # the two normalised columns are exact opposites, the loss divides by their sum (= 0) and every gradient is NaN
+    wo = [(rng.standard_normal((Fo, T)) * np.sqrt(2.0 / (Fo + T))).astype(np.float32), np.zeros(T, np.float32)]
+    return dict(arcs=arcs, nodes=nodes, targets=targets, x0=x0, ws=ws, wo=wo, src=src, dst=dst, NL=NL, AL=AL, T=T, DS=DS, N=N,
+                E=int(dst.shape[0]))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# clocks sampling during the timed region
+# ---------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = 'clocks.sm,clocks.max.sm,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,' \
+            'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index: int = 0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--id={self.index}', f'--query-gpu={self.QUERY}', '--format=csv,noheader,nounits',
+                                          '-lms', '200'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout: self.rows.append([c.strip() for c in line.split(',')])
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            self.proc.terminate()
+            try: self.proc.wait(timeout=2)
+            except Exception: self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, flag in zip(names, r[3:7]):
+                if flag.lower().startswith('active'): reasons.add(name)
+        if not sm: return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        return {'sm_mhz': float(np.median(sm)), 'sm_max_mhz': float(max(mx)), 'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU port (oracle) -- cpu_baseline leg and --impl reference
+# ---------------------------------------------------------------------------------------------------------------------
+def cpu_port_run(wl, iterations: int, repeats: int = 1):
+    """ forward loop of the oracle restatement (torch-CPU, all host threads) for `iterations` iterations of the workload.
+    :return: (arc-updates per second, seconds per run, threads) """
+    import torch
+    from oracle import gnn_oracle as O
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    g = O.OracleGraph.build(wl['arcs'], wl['nodes'], wl['targets'], 'n', None, None, 1, None, 'average', endpoints=(wl['src'], wl['dst']))
+    net_s = O.OracleMLP.from_weights(wl['ws'], ['selu'], batchnorm=True, requires_grad=False)
+    net_o = O.OracleMLP.from_weights(wl['wo'], ['softmax'], batchnorm=False, requires_grad=False)
+    x0 = torch.from_numpy(wl['x0'])
+    best = float('inf')
+    k = 0
+    for rep in range(repeats + 1):   # first run warms the CSR cache / allocator and is not timed
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            k = O.loop(g, net_s, net_o, state_vect_dim=wl['DS'], max_iteration=iterations, threshold=0.0, x0=x0, fast_spmm=True)[0]
+        dt = time.perf_counter() - t0
+        if rep > 0: best = min(best, dt)
+    return wl['E'] * k / best, best, threads
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='c4u', choices=['c4u', 'c4l'])
+    ap.add_argument('--nodes', type=int, default=1_000_000)
+    ap.add_argument('--arcs', type=int, default=10_000_000)
+    ap.add_argument('--max-iter', type=int, default=50)
+    ap.add_argument('--cpu-iterations', type=int, default=3, help='iterations of the workload timed on the CPU port')
+    ap.add_argument('--skip-train', action='store_true')
+    ap.add_argument('--skip-cpu', action='store_true')
+    args = ap.parse_args()
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    metric = 'arc-updates/sec (arcs x iterations), state-convergence loop forward, 10M-arc graph'
+    config = {'workload': f'{args.workload}: single synthetic graph, {args.nodes} nodes / {args.arcs} arcs, in-degree {args.arcs // args.nodes}, '
+                          f'state_dim 32, NL 3, AL 1, max_iteration {args.max_iter}, threshold 0 (k = max_iteration), '
+                          f'net_state Dense(71->32, selu)+BatchNormalization, aggregation average',
+              'l2': 'inputs larger than L2 (state 2 x 128 MB + 40 MB arc indices per iteration)', 'seed': 0}
+
+    # ---------------- reference arm: the CPU port of the reference path on the host cores -----------------------------
+    if args.impl == 'reference':
+        if rank != 0: return
+        wl = make_workload(args.workload, args.nodes, args.arcs)
+        vals = []
+        for _ in range(max(1, args.warmup > 0) + args.steps):
+            v, sec, threads = cpu_port_run(wl, args.cpu_iterations, repeats=1)
+            vals.append((v, sec))
+        vals = vals[1:] if len(vals) > 1 else vals
+        value = float(np.mean([v for v, _ in vals]))
+        ms = float(np.mean([s for _, s in vals])) * 1e3
+        sample = f'{args.cpu_iterations} iterations of the forward loop on the full {args.workload} graph per step (of {args.max_iter})'
+        print(json.dumps({'impl': 'reference', 'metric': metric, 'value': value, 'unit': 'arc-updates/s', 'n_gpus': args.gpus,
+                          'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'strong',
+                          'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': config,
+                          'cpu_baseline': {'value': value, 'unit': 'arc-updates/s', 'cores': threads, 'kind': 'port', 'sample': sample,
+                                           'note': 'torch-CPU restatement of the reference TF2 path (oracle/), not TensorFlow'},
+                          'e2e': {'value': value, 'unit': 'arc-updates/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
+        return
+
+    # ---------------- our arm -----------------------------------------------------------------------------------------
+    import torch
+    import gnn_b200
+    from gnn_b200 import _native
+    from gnn_b200.graph_class import GraphObject, GraphTensor
+    from gnn_b200.GNN import GNNnodeBased
+    from gnn_b200.keras_compat import Dense, BatchNormalization, Sequential, Adam, categorical_crossentropy
+    if not torch.cuda.is_available(): raise SystemExit('bench.py needs a CUDA device')
+    torch.cuda.set_device(local_rank)
+    device = torch.device('cuda', local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=device)
+
+    from gnn_b200 import dist_graph
+    wl = make_workload(args.workload, args.nodes, args.arcs)
+    N, E = wl['N'], wl['E']
+
+    def build_gnn():
+        net_s = Sequential([Dense(wl['DS'], activation='selu'), BatchNormalization()], input_dim=wl['AL'] + 2 * (wl['NL'] + wl['DS']), device=device)
+        net_o = Sequential([Dense(wl['T'], activation='softmax')], input_dim=wl['NL'] + wl['DS'], device=device)
+        net_s.set_weights(wl['ws']); net_o.set_weights(wl['wo'])
+        gnn = GNNnodeBased(net_s, net_o, Adam(1e-3), categorical_crossentropy, {'from_logits': False}, state_vect_dim=wl['DS'],
+                           max_iteration=args.max_iter, threshold=0.0, addressed_problem='c', path_writer=f'/tmp/gnn_b200_bench_{rank}/')
+        gnn.initial_state = torch.as_tensor(wl['x0'], device=device)
+        return gnn
+
+    g_host = GraphObject(arcs=wl['arcs'], nodes=wl['nodes'], targets=wl['targets'], problem_based='n', aggregation_mode='average',
+                         _endpoints=(wl['src'], wl['dst']))
+    if world > 1:
+        result = dist_graph.bench_partitioned(g_host, wl, build_gnn, args, device, rank, world)
+        if rank == 0:
+            result.update({'metric': metric, 'unit': 'arc-updates/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+                           'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': config})
+            print(json.dumps(result))
+        dist.destroy_process_group()
+        return
+
+    gnn = build_gnn()
+    gt = GraphTensor.fromGraphObject(g_host, device=device)
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup): fn()
+        torch.cuda.synchronize()
+        start.record()
+        for _ in range(steps): fn()
+        stop.record()
+        torch.cuda.synchronize()
+        return start.elapsed_time(stop) / steps
+
+    # --- value: forward loop, inputs resident ---------------------------------------------------------------------
+    ks = []
+
+    def fwd():
+        with torch.no_grad():
+            k, state, out = gnn.Loop(gt, training=False)
+        ks.append(k)
+
+    with ClockSampler(local_rank) as clocks:
+        _native.launch_count(reset=True)
+        ms_fwd = timed(fwd, args.steps, max(3, args.warmup))
+        launches_fwd = _native.launch_count() * args.steps // (args.steps + max(3, args.warmup))
+        k_fwd = float(ks[-1])
+        value = E * k_fwd / (ms_fwd * 1e-3)
+
+        # --- roofline: the fused iteration kernel alone (events inside the library, launching stream) --------------
+        _native.profile_iterations(True)
+        iter_ms = []
+        for _ in range(args.steps):
+            fwd()
+            ms, n_launch = _native.profile_last_iterations()
+            iter_ms.append(ms / max(n_launch, 1))
+        _native.profile_iterations(False)
+    kernel_ms = float(np.mean(iter_ms))
+    alg_bytes = algorithmic_bytes_per_iteration(N, E, wl['DS'], wl['NL'], wl['AL'])
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f: peaks = json.load(f)
+    except Exception:
+        pass
+    peak_gbs = float(peaks.get('hbm_gbs', 6650.0))
+    achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+    roofline = {'bound': 'hbm', 'kernel': 'state_iter_kernel<32,false,128,128>', 'achieved': achieved, 'peak': peak_gbs, 'unit': 'GB/s',
+                'frac': achieved / peak_gbs, 'traffic': None, 'peak_source': 'MEASURED_PEAKS.json' if peaks else 'fallback 6650 GB/s',
+                'algorithmic_bytes_per_launch': alg_bytes, 'bytes_per_arc_update': alg_bytes / E, 'ms_per_launch': kernel_ms}
+    traffic_file = os.path.join(ROOT, 'profiles', 'traffic_bytes_per_launch.json')
+    if os.path.exists(traffic_file):
+        with open(traffic_file) as f: roofline['traffic'] = json.load(f).get(args.workload)
+
+    # --- e2e: host buffers -> gnn(GraphObject) -> host outputs, every step -----------------------------------------
+    g_host.pin_host_buffers()
+    x0_host = torch.from_numpy(wl['x0']).pin_memory()
+    h2d = g_host.host_bytes() + x0_host.numel() * 4
+    d2h_holder = []
+
+    def e2e_step():
+        gnn.initial_state = x0_host.to(device, non_blocking=True)
+        out = gnn(g_host)
+        d2h_holder.append(out.cpu())
+        if len(d2h_holder) > 2: d2h_holder.pop(0)
+
+    ms_e2e = timed(e2e_step, args.steps, 1)
+    e2e = {'value': E * k_fwd / (ms_e2e * 1e-3), 'unit': 'arc-updates/s', 'ms_per_step': ms_e2e, 'h2d_bytes_per_step': int(h2d),
+           'd2h_bytes_per_step': int(d2h_holder[-1].numel() * 4)}
+    gnn.initial_state = torch.as_tensor(wl['x0'], device=device)
+
+    # --- train: forward + BPTT backward + optimizer (= one epoch of this one-graph dataset) -------------------------
+    train = None
+    if not args.skip_train:
+        kt = []
+
+        def train_step():
+            iters, _ = gnn.training_step(gt, mean=True)
+            kt.append(iters[0])
+
+        _native.launch_count(reset=True)
+        ms_train = timed(train_step, max(1, args.steps // 2), 1)
+        train = {'value': E * float(kt[-1]) / (ms_train * 1e-3), 'unit': 'arc-updates/s (forward+backward+Adam)', 'ms_per_step': ms_train,
+                 'epoch_time_s': ms_train * 1e-3, 'k': float(kt[-1])}
+
+    # --- CPU baseline: oracle port on the host cores, bounded sample ----------------------------------------------
+    cpu = None
+    if not args.skip_cpu:
+        v, sec, threads = cpu_port_run(wl, args.cpu_iterations, repeats=1)
+        cpu = {'value': v, 'unit': 'arc-updates/s', 'cores': threads, 'kind': 'port',
+               'sample': f'{args.cpu_iterations} iterations of the forward loop on the full {args.workload} graph ({sec:.2f} s)',
+               'note': 'torch-CPU restatement of the reference TF2 path (oracle/), not TensorFlow'}
+
+    print(json.dumps({'metric': metric, 'value': value, 'unit': 'arc-updates/s', 'n_gpus': 1, 'steps': args.steps, 'warmup': max(3, args.warmup),
+                      'ms_per_step': ms_fwd, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32',
+                      'data': 'synthetic', 'config': config, 'iterations': k_fwd, 'e2e': e2e, 'gpu_launches': int(launches_fwd),
+                      'roofline': roofline, 'train': train, 'cpu_baseline': cpu, 'clocks': clocks.summary()}))
+
+
+if __name__ == '__main__':
+    main()

@@ -56,7 +56,7 @@ class gnn_loop_args(C.Structure):
 # every symbol include/gnn_b200.h declares (tests check that the library exports all of them)
 EXPORTED_SYMBOLS = ['gnn_last_error', 'gnn_abi_version', 'gnn_device_info', 'gnn_csr_build', 'gnn_spmm',
                     'gnn_state_loop_workspace_bytes', 'gnn_state_loop_forward', 'gnn_state_loop_backward',
-                    'gnn_launch_count']
+                    'gnn_launch_count', 'gnn_profile_iterations', 'gnn_profile_last_iterations']
 
 
 def library_path() -> str: return _LIB_PATH
@@ -88,7 +88,9 @@ def lib() -> C.CDLL:
         l.gnn_state_loop_backward.argtypes = [C.POINTER(gnn_graph), C.POINTER(gnn_mlp), C.POINTER(gnn_loop_args), C.c_void_p,
                                               C.POINTER(gnn_mlp_grad), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                               C.c_void_p, C.c_size_t, C.c_void_p]
-        for name in ('gnn_device_info', 'gnn_csr_build', 'gnn_spmm', 'gnn_state_loop_workspace_bytes',
+        l.gnn_profile_iterations.argtypes = [C.c_int32]
+        l.gnn_profile_last_iterations.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_int32)]
+        for name in ('gnn_profile_iterations', 'gnn_profile_last_iterations', 'gnn_device_info', 'gnn_csr_build', 'gnn_spmm', 'gnn_state_loop_workspace_bytes',
                      'gnn_state_loop_forward', 'gnn_state_loop_backward'):
             getattr(l, name).restype = C.c_int
         _lib = l
@@ -112,6 +114,17 @@ def _stream(device) -> int:
 
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
+
+
+def profile_iterations(enable: bool) -> None:
+    check(lib().gnn_profile_iterations(1 if enable else 0), 'gnn_profile_iterations')
+
+
+def profile_last_iterations() -> tuple[float, int]:
+    """ (milliseconds between the first and the last iteration-kernel launch of the last forward, launches) """
+    ms, n = C.c_float(0), C.c_int32(0)
+    check(lib().gnn_profile_last_iterations(C.byref(ms), C.byref(n)), 'gnn_profile_last_iterations')
+    return float(ms.value), int(n.value)
 
 
 def launch_count(reset: bool = False) -> int:

@@ -229,7 +229,7 @@ extern "C" int gnn_spmm(const int32_t* rowptr, const int32_t* col, const float* 
     cudaStream_t stream = (cudaStream_t)stream_;
     if (n_rows < 0 || F < 0) GNN_FAIL(GNN_ERR_INVALID, "gnn_spmm: bad sizes");
     if (n_rows == 0 || F == 0) return GNN_OK;
-    if (!rowptr || !col || !dense || !out) GNN_FAIL(GNN_ERR_INVALID, "gnn_spmm: NULL argument");
+    if (!rowptr || !out) GNN_FAIL(GNN_ERR_INVALID, "gnn_spmm: NULL argument");  // col / dense may be NULL when there are no entries
     int64_t items = n_rows * ((F + 3) / 4);
     spmm_kernel<<<(unsigned)ceil_div(items, 256), 256, 0, stream>>>(rowptr, col, val, n_rows, dense, ld_dense, F, out, ld_out, accumulate);
     GNN_LAUNCH_CHECK();

@@ -121,13 +121,80 @@ __device__ __forceinline__ float4 gather_rows(const float* __restrict__ x_in, in
     return acc;
 }
 
+#ifndef GNN_GATHER_BATCH
+#define GNN_GATHER_BATCH 8
+#endif
+#ifndef GNN_FWD_MIN_CTAS
+#define GNN_FWD_MIN_CTAS 1
+#endif
+
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gmem_src) {
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
 __device__ __forceinline__ float drop1(float v, bool active, uint32_t key, uint64_t idx, float rate, float scale) {
     if (!active) return v;
     return dropout_keep(key, idx, rate) ? v * scale : 0.f;
 }
 
+// Segment sums of NPG consecutive nodes (i0 .. i0+NPG-1 of the tile) by one lane group: the arcs of those nodes
+// are one contiguous range [srow[i0], srow[i0+NPG]) walked in batches of GB.  Per batch: (1) all source indices
+// (and weights), (2) all GB row loads back to back -- nothing with a scoreboard in between, so they overlap --
+// (3) accumulation in stored order, flushing the sum of a node to the tile when the walk crosses its row pointer.
+// cols / vals are indexed by the GLOBAL arc position (the caller pre-offsets the shared-memory copies).
+template <int DP, bool HAS_VAL, bool STAGED, int GB, int NPG>
+__device__ __forceinline__ void gather_group(const float* __restrict__ x_in, const int32_t* cols, const float* vals,
+                                             const int* srow, const float* sscale, int i0, int lig, int nvalid,
+                                             float* tile_agg, int SA, float* agg_save) {
+    int i = i0;
+    int e = srow[i0];
+    const int eend = srow[i0 + NPG];
+    int next = srow[i0 + 1];
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto flush = [&]() {
+        if (!HAS_VAL) {
+            const float sc = sscale[i];
+            acc.x *= sc; acc.y *= sc; acc.z *= sc; acc.w *= sc;
+        }
+        if (agg_save && i < nvalid) st4(agg_save + (size_t)i * DP + 4 * lig, acc);
+        st4(tile_agg + i * SA + 4 * lig, acc);
+        acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        ++i;
+        next = srow[i + 1 <= i0 + NPG ? i + 1 : i0 + NPG];
+    };
+    const float* xl = x_in + 4 * lig;
+    while (e < eend) {
+        int idx[GB];
+        float w[GB];
+        float4 r[GB];
+#pragma unroll
+        for (int b = 0; b < GB; ++b) {   // (1) indices: past the end -> repeat the last arc (its row is loaded, not summed)
+            const int ee = min(e + b, eend - 1);
+            idx[b] = STAGED ? cols[ee] : __ldg(cols + ee);
+            if (HAS_VAL) w[b] = STAGED ? vals[ee] : __ldg(vals + ee);
+        }
+#pragma unroll
+        for (int b = 0; b < GB; ++b) r[b] = ldg4(xl + (size_t)idx[b] * DP);   // (2) GB loads in flight
+#pragma unroll
+        for (int b = 0; b < GB; ++b) {   // (3) stored-order accumulation
+            const int ee = e + b;
+            if (ee < eend) {
+                while (ee >= next) flush();
+                if (HAS_VAL) acc = fma4(w[b], r[b], acc);
+                else acc = add4(acc, r[b]);
+            }
+        }
+        e += GB;
+    }
+    while (i < i0 + NPG) flush();
+}
+
 template <int DP, bool HAS_VAL, int TN, int NT>
-__global__ void __launch_bounds__(NT) state_iter_kernel(const IterParams p) {
+__global__ void __launch_bounds__(NT, GNN_FWD_MIN_CTAS) state_iter_kernel(const IterParams p) {
+    constexpr int GB = GNN_GATHER_BATCH;  // arcs in flight per lane
     static_assert(TN % 32 == 0 && NT % 32 == 0 && TN % 8 == 0, "tile shape");
     constexpr int LPN = DP / 4;          // lanes per node row
     constexpr int NGRP = NT / LPN;       // node rows gathered concurrently by a CTA
@@ -147,6 +214,7 @@ __global__ void __launch_bounds__(NT) state_iter_kernel(const IterParams p) {
     int* scol = srow + ((TN + 1 + 3) & ~3);
     float* sval = reinterpret_cast<float*>(scol + p.scol_cap);
     __shared__ int s_flag;
+    __shared__ float sscale[TN];  // per-node arc weight of the tile (row-scale mode)
 
     for (int i = tid * 4; i < net.fwd_floats; i += NT * 4) st4(sW + i, ldg4(p.wpack + i));
     if (tid == 0) s_flag = 0;
@@ -166,6 +234,8 @@ __global__ void __launch_bounds__(NT) state_iter_kernel(const IterParams p) {
         const int nvalid = (int)min((long long)TN, p.N - n0);
         __syncthreads();  // previous tile fully consumed (also orders the weight staging on the first pass)
         for (int i = tid; i <= TN; i += NT) srow[i] = __ldg(p.rowptr + min(n0 + i, p.N));
+        if (!HAS_VAL)
+            for (int i = tid; i < TN; i += NT) sscale[i] = i < nvalid ? __ldg(p.cst + (size_t)(n0 + i) * CP + net.C) : 0.f;
         __syncthreads();
         const int ebase = srow[0];
         const int ecount = srow[TN] - ebase;
@@ -179,55 +249,55 @@ __global__ void __launch_bounds__(NT) state_iter_kernel(const IterParams p) {
         __syncthreads();
 
         // ---- 2. gather ------------------------------------------------------------------------------
-        for (int i = grp; i < TN; i += NGRP) {
-            float* rowA = bufA + i * SA;
-            if (i >= nvalid) {  // rows past the end: defined zeros
-                const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-                st4(rowA + 4 * lig, z);
-                st4(rowA + DP + 4 * lig, z);
-                for (int c = lig; c < CP / 4; c += LPN) st4(rowA + 2 * DP + 4 * c, z);
-                continue;
-            }
-            const long long n = n0 + i;
-            const int e0 = srow[i], e1 = srow[i + 1];
-            float4 agg = staged ? gather_rows<DP, HAS_VAL, true>(p.x_in, 4 * lig, e0 - ebase, e1 - ebase, scol, sval)
-                                : gather_rows<DP, HAS_VAL, false>(p.x_in, 4 * lig, e0, e1, p.col, p.val);
-            float4 own = ldg4(p.x_in + (size_t)n * DP + 4 * lig);
-            if (!HAS_VAL) {
-                const float s = __ldg(p.cst + (size_t)n * CP + net.C);
-                agg.x *= s; agg.y *= s; agg.z *= s; agg.w *= s;
-            }
-            if (p.agg_save) st4(p.agg_save + (size_t)n * DP + 4 * lig, agg);
-            if (drop_in) {
-                const uint64_t rbase = (uint64_t)n * (uint64_t)F_in;
-                float* o = reinterpret_cast<float*>(&own);
-                float* a = reinterpret_cast<float*>(&agg);
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const int j = 4 * lig + c;
-                    if (j < D) {
-                        o[c] = drop1(o[c], true, key_in, rbase + j, net.drop[0], scale_in);
-                        a[c] = drop1(a[c], true, key_in, rbase + D + net.NL_self + j, net.drop[0], scale_in);
-                    }
-                }
-            }
-            st4(rowA + 4 * lig, own);
-            st4(rowA + DP + 4 * lig, agg);
-            for (int c = lig; c < CP / 4; c += LPN) {
-                float4 v = ldg4(p.cst + (size_t)n * CP + 4 * c);
-                if (drop_in) {
-                    const uint64_t rbase = (uint64_t)n * (uint64_t)F_in;
-                    float* vv = reinterpret_cast<float*>(&v);
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const int kc = keras_input_col(2 * DP + 4 * c + q, D, DP, net.NL_self, net.NL_agg, net.AL);
-                        if (kc >= 0) vv[q] = drop1(vv[q], true, key_in, rbase + kc, net.drop[0], scale_in);
-                    }
-                }
-                st4(rowA + 2 * DP + 4 * c, v);
-            }
+        // (a) own state rows and constant rows: asynchronous 16-byte copies straight into the tile (no registers)
+        for (int item = tid; item < TN * LPN; item += NT) {
+            const int i = item / LPN;
+            float* dstp = bufA + i * SA + 4 * lig;
+            if (i < nvalid) cp_async16(dstp, p.x_in + (size_t)(n0 + i) * DP + 4 * lig);
+            else st4(dstp, make_float4(0.f, 0.f, 0.f, 0.f));
         }
+        for (int item = tid; item < TN * (CP / 4); item += NT) {
+            const int i = item / (CP / 4), c = item % (CP / 4);
+            float* dstp = bufA + i * SA + 2 * DP + 4 * c;
+            if (i < nvalid) cp_async16(dstp, p.cst + (size_t)(n0 + i) * CP + 4 * c);
+            else st4(dstp, make_float4(0.f, 0.f, 0.f, 0.f));
+        }
+        cp_async_commit();
+
+        // (b) segment sums: a lane group owns NPG consecutive nodes and walks their arcs as ONE flat list in batches of
+        //     GB arcs -- GB independent 128-bit loads in flight per lane whatever the degrees are; the running sum is
+        //     flushed to the tile whenever the walk crosses a row pointer (stored order => deterministic)
+        {
+            constexpr int NPG = TN / NGRP;
+            float* agg_dst = p.agg_save ? p.agg_save + (size_t)n0 * DP : nullptr;
+            if (staged)
+                gather_group<DP, HAS_VAL, true, GB, NPG>(p.x_in, scol - ebase, sval - ebase, srow, sscale, grp * NPG, lig, nvalid,
+                                                         bufA + DP, SA, agg_dst);
+            else
+                gather_group<DP, HAS_VAL, false, GB, NPG>(p.x_in, p.col, p.val, srow, sscale, grp * NPG, lig, nvalid, bufA + DP,
+                                                          SA, agg_dst);
+        }
+        cp_async_wait_all();
         __syncthreads();
+
+        // (c) input dropout (training, Dropout in front of the first Dense): mask the assembled rows in place
+        if (drop_in) {
+            for (int item = tid; item < TN * (KP / 4); item += NT) {
+                const int i = item / (KP / 4), c = item % (KP / 4);
+                if (i >= nvalid) continue;
+                float* q = bufA + i * SA + 4 * c;
+                float4 v = ld4(q);
+                float* vv = reinterpret_cast<float*>(&v);
+                const uint64_t rbase = (uint64_t)(n0 + i) * (uint64_t)F_in;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int kc = keras_input_col(4 * c + u, D, DP, net.NL_self, net.NL_agg, net.AL);
+                    if (kc >= 0) vv[u] = drop1(vv[u], true, key_in, rbase + kc, net.drop[0], scale_in);
+                }
+                st4(q, v);
+            }
+            __syncthreads();
+        }
 
         // ---- 3. MLP ---------------------------------------------------------------------------------
         // hidden layers alternate bufB / bufA+DP; the last layer writes bufA + final_off.  When final_off == DP
@@ -255,23 +325,12 @@ __global__ void __launch_bounds__(NT) state_iter_kernel(const IterParams p) {
             const float* aff_c = aff_a + HP;
             const bool affine = last && !p.bn_train;
 
+            // the register-blocked product only stores raw pre-activations; bias, activation, dropout and the final
+            // affine run as one element-wise pass over the tile (keeps the unrolled code small)
             auto epi = [&](int ng, int cg, float (&acc)[8][4]) {
-                const float4 b4 = ld4(bias + 4 * cg);
-                const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int row = ng + NG * i;
-                    float v[4];
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        const int j = 4 * cg + c;
-                        float y = act_apply(act, acc[i][c] + bb[c]);
-                        if (drop_here) y = drop1(y, j < odim, key, (uint64_t)(n0 + row) * (uint64_t)odim + j, rate, dscale);
-                        if (affine) y = fmaf(aff_a[j], y, aff_c[j]);
-                        v[c] = (j < odim) ? y : 0.f;
-                    }
-                    st4(out + row * out_stride + 4 * cg, make_float4(v[0], v[1], v[2], v[3]));
-                }
+                for (int i = 0; i < 8; ++i)
+                    st4(out + (ng + NG * i) * out_stride + 4 * cg, make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));
             };
             if (hazard) {
                 const int CG = HP >> 2;
@@ -283,6 +342,26 @@ __global__ void __launch_bounds__(NT) state_iter_kernel(const IterParams p) {
                 if (has_work) epi(ng, cg, acc);
             } else {
                 dense_tile<TN, NT>(in, in_stride, net.in_pad[l], W, HP, epi);
+            }
+            __syncthreads();
+            {
+                const int CG = HP >> 2;
+                for (int item = tid; item < TN * CG; item += NT) {
+                    const int row = item / CG, cg = item % CG;
+                    float* q = out + row * out_stride + 4 * cg;
+                    float4 v4 = ld4(q);
+                    const float4 b4 = ld4(bias + 4 * cg);
+                    float v[4] = {v4.x + b4.x, v4.y + b4.y, v4.z + b4.z, v4.w + b4.w};
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const int j = 4 * cg + c;
+                        float y = act_apply(act, v[c]);
+                        if (drop_here) y = drop1(y, j < odim, key, (uint64_t)(n0 + row) * (uint64_t)odim + j, rate, dscale);
+                        if (affine) y = fmaf(aff_a[j], y, aff_c[j]);
+                        v[c] = (j < odim) ? y : 0.f;
+                    }
+                    st4(q, make_float4(v[0], v[1], v[2], v[3]));
+                }
             }
             __syncthreads();
         }

@@ -11,6 +11,15 @@
 namespace gnn {
 namespace {
 
+// optional event bracketing of the iteration launches (gnn_profile_iterations)
+struct IterProfile {
+    bool enabled = false;
+    cudaEvent_t begin = nullptr, end = nullptr;
+    int launches = 0;
+    bool pending = false;
+};
+static IterProfile g_profile;
+
 struct DeviceInfo {
     int sms = 0, smem_optin = 0;
 };
@@ -171,15 +180,23 @@ int make_plan(const gnn_graph* g, const gnn_mlp* net, const gnn_loop_args* a, Pl
     if (!plan->kernel) GNN_FAIL(GNN_ERR_UNSUPPORTED, "no kernel for padded state width %d", lay.DP);
     const int TN = plan->ts.tn;
     const size_t fixed = ((size_t)lay.fwd_floats + (size_t)TN * lay.SA + (size_t)TN * lay.SB + ((TN + 1 + 3) & ~3)) * 4;
-    // arc indices of a tile are staged in shared memory when they fit: ~1.6x the average tile
-    long long avg = g->n_nodes > 0 ? (g->n_arcs * TN) / g->n_nodes : 0;
-    int cap = (int)std::min<long long>(8192, std::max<long long>(256, (avg * 8 / 5 + 255) / 256 * 256));
+    // arc indices of a tile are staged in shared memory when they fit. Two candidate capacities (1.6x and 1.2x the
+    // average tile): the smaller one wins when it lets one more CTA live on an SM
+    const long long avg = g->n_nodes > 0 ? (g->n_arcs * TN) / g->n_nodes : 0;
     const size_t per_arc = plan->has_val ? 8 : 4;
-    while (cap > 0 && fixed + cap * per_arc > (size_t)di.smem_optin) cap /= 2;
     if (fixed > (size_t)di.smem_optin)
         GNN_FAIL(GNN_ERR_UNSUPPORTED, "net_state too large for shared memory: %zu bytes needed, %d available", fixed, di.smem_optin);
-    plan->scol_cap = cap;
-    plan->smem = fixed + cap * per_arc;
+    int best_cap = 0, best_occ = 0;
+    const long long wanted[2] = {(avg * 8 / 5 + 255) / 256 * 256, (avg * 6 / 5 + 127) / 128 * 128};
+    for (int c = 0; c < 2; ++c) {
+        int cap = (int)std::min<long long>(8192, std::max<long long>(256, wanted[c]));
+        while (cap > 0 && fixed + cap * per_arc > (size_t)di.smem_optin) cap /= 2;
+        int occ = 0;
+        GNN_TRY(kernel_occupancy((const void*)plan->kernel, plan->ts.nt, fixed + cap * per_arc, &occ));
+        if (occ > best_occ) { best_occ = occ; best_cap = cap; }
+    }
+    plan->scol_cap = best_cap;
+    plan->smem = fixed + best_cap * per_arc;
     int occ = 0;
     GNN_TRY(kernel_occupancy((const void*)plan->kernel, plan->ts.nt, plan->smem, &occ));
     long long ntiles = (g->n_nodes + TN - 1) / TN;
@@ -249,6 +266,10 @@ extern "C" int gnn_state_loop_forward(const gnn_graph* g, const gnn_mlp* net, co
     p.bn_train = bn_train; p.seed = a->seed; p.training = a->training; p.scol_cap = plan.scol_cap; p.net = lay;
     BnApplyKernel bn_apply = kernel_set(lay.DP)->bn_apply;
 
+    if (g_profile.enabled) {
+        GNN_CUDA(cudaEventRecord(g_profile.begin, stream));
+        g_profile.launches = 0;
+    }
     for (int t = 0; t < a->max_iter; ++t) {
         const float* x_in = w.X + (size_t)(save ? t : (t & 1)) * w.slab;
         float* x_next = w.X + (size_t)(save ? t + 1 : ((t + 1) & 1)) * w.slab;
@@ -261,6 +282,7 @@ extern "C" int gnn_state_loop_forward(const gnn_graph* g, const gnn_mlp* net, co
         void* args[] = {(void*)&p};
         GNN_CUDA(cudaLaunchKernel((const void*)plan.kernel, dim3(plan.grid), dim3(plan.ts.nt), args, plan.smem, stream));
         GNN_LAUNCH_CHECK();
+        if (g_profile.enabled) ++g_profile.launches;
         if (bn_train) {
             float* stats = w.stats + (size_t)t * 4 * lay.DP;
             bn_stats_kernel<<<(lay.DP + 31) / 32, 32, 0, stream>>>(go + t, w.bn_partial, plan.grid, lay.DP, lay.D, N, net->bn_gamma,
@@ -272,9 +294,34 @@ extern "C" int gnn_state_loop_forward(const gnn_graph* g, const gnn_mlp* net, co
             GNN_LAUNCH_CHECK();
         }
     }
+    if (g_profile.enabled) {
+        GNN_CUDA(cudaEventRecord(g_profile.end, stream));
+        g_profile.pending = true;
+    }
     finalize_kernel<<<(unsigned)ceil_div(std::max<long long>(N * lay.D, 1), 256), 256, 0, stream>>>(
         kptr, w.X, (long long)w.slab, save ? 0 : 2, N, lay.D, lay.DP, a->x_out, a->k_out);
     GNN_LAUNCH_CHECK();
+    return GNN_OK;
+}
+
+extern "C" int gnn_profile_iterations(int32_t enable) {
+    if (enable && !g_profile.begin) {
+        GNN_CUDA(cudaEventCreate(&g_profile.begin));
+        GNN_CUDA(cudaEventCreate(&g_profile.end));
+    }
+    g_profile.enabled = enable != 0;
+    g_profile.pending = false;
+    return GNN_OK;
+}
+
+extern "C" int gnn_profile_last_iterations(float* elapsed_ms, int32_t* launches) {
+    if (!g_profile.pending) GNN_FAIL(GNN_ERR_INVALID, "no profiled forward call is pending");
+    GNN_CUDA(cudaEventSynchronize(g_profile.end));
+    float ms = 0.f;
+    GNN_CUDA(cudaEventElapsedTime(&ms, g_profile.begin, g_profile.end));
+    if (elapsed_ms) *elapsed_ms = ms;
+    if (launches) *launches = g_profile.launches;
+    g_profile.pending = false;
     return GNN_OK;
 }
 

@@ -119,6 +119,31 @@ class GraphObject:
                            ArcNode=self.getArcNode(), aggregation_mode=self.aggregation_mode,
                            _endpoints=(self._src.copy(), self._dst.copy()))
 
+    def pin_host_buffers(self) -> None:
+        """ move the arrays that GraphTensor.fromGraphObject copies to the device into page-locked host memory
+        (numpy views over pinned torch storage), so that the host->device copies run at full PCIe/NVLink-C2C speed """
+        import torch
+        if not torch.cuda.is_available(): return
+        self._pinned = getattr(self, '_pinned', dict())
+
+        def pin(name, arr):
+            t = torch.from_numpy(np.ascontiguousarray(arr)).pin_memory()
+            self._pinned[name] = t
+            return t.numpy()
+
+        self.arcs, self.nodes, self.targets = pin('arcs', self.arcs), pin('nodes', self.nodes), pin('targets', self.targets)
+        for name in ('Adjacency', 'ArcNode'):
+            m = getattr(self, name)
+            m.row, m.col, m.data = pin(name + '.row', m.row.astype(np.int32)), pin(name + '.col', m.col.astype(np.int32)), \
+                pin(name + '.data', m.data)
+
+    def host_bytes(self) -> int:
+        """ bytes GraphTensor.fromGraphObject copies host->device for this graph """
+        total = self.arcs.nbytes + self.nodes.nbytes + self.targets.nbytes + self.set_mask.nbytes + self.output_mask.nbytes
+        total += 4 * self.sample_weights.shape[0]
+        for m in (self.Adjacency, self.ArcNode): total += 4 * (len(m.row) + len(m.col) + len(m.data))
+        return int(total)
+
     ## STRUCTURE BUILDERS #############################################################################################
     def buildArcNode(self):
         """ ArcNode COO of shape (E, N): entry (arc i, dst(i)) = aggregation weight (graph_class.py:98-121).

@@ -45,7 +45,7 @@ def sparse_dense(sp: SparseCSR, dense: torch.Tensor) -> torch.Tensor:
 
 
 class _LoopConfig:
-    __slots__ = ('adj', 'net', 'spec', 'D', 'NL_self', 'NL_agg', 'AL', 'max_iter', 'threshold', 'training', 'seed')
+    __slots__ = ('adj', 'net', 'spec', 'D', 'NL_self', 'NL_agg', 'AL', 'max_iter', 'threshold', 'training', 'seed', 'save')
 
 
 class _StateLoop(torch.autograd.Function):
@@ -58,8 +58,7 @@ class _StateLoop(torch.autograd.Function):
         x0c = x0.detach().contiguous()
         nodes_c = None if nodes is None else nodes.detach().contiguous()
         agg_nodes_c, agg_arcs_c = agg_nodes.detach().contiguous(), agg_arcs.detach().contiguous()
-        needs_grad = any(t is not None and t.requires_grad for t in (x0, nodes, agg_nodes, agg_arcs) + tuple(params))
-        save = bool(needs_grad and torch.is_grad_enabled())
+        save = cfg.save   # decided by the caller: grad mode is always off inside Function.forward
 
         keep = []
         mlp = N.make_mlp(cfg.spec, keep)
@@ -168,5 +167,8 @@ def state_loop(adjacency: SparseCSR, net_state: Sequential, x0: torch.Tensor, no
                          f'{2 * cfg.D + cfg.NL_self + cfg.NL_agg + cfg.AL} = AL + 2*(NL + state_vect_dim)')
     if cfg.spec.dims[-1] != cfg.D:
         raise ValueError(f'net_state output width {cfg.spec.dims[-1]} != state width {cfg.D}')
-    x, k = _StateLoop.apply(cfg, x0.to(torch.float32), nodes, aggregated_nodes, aggregated_arcs, *net_state.trainable_variables)
+    params = net_state.trainable_variables
+    cfg.save = bool(torch.is_grad_enabled() and any(t is not None and t.requires_grad
+                                                    for t in [x0, nodes, aggregated_nodes, aggregated_arcs] + list(params)))
+    x, k = _StateLoop.apply(cfg, x0.to(torch.float32), nodes, aggregated_nodes, aggregated_arcs, *params)
     return k, x

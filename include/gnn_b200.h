@@ -162,6 +162,13 @@ int gnn_state_loop_backward(const gnn_graph* g, const gnn_mlp* net, const gnn_lo
 /* number of kernels the library has launched since the last reset (for bench.py's gpu_launches) */
 int64_t gnn_launch_count(int32_t reset);
 
+/* Measurement aid for bench.py's roofline: when enabled, gnn_state_loop_forward brackets the sequence of
+ * iteration-kernel launches (not the prologue / epilogue kernels) with CUDA events on the launching stream.
+ * gnn_profile_last_iterations waits for the closing event and returns the elapsed milliseconds and the number of
+ * iteration launches enqueued between the two events (launches that found the loop stopped return at once). */
+int gnn_profile_iterations(int32_t enable);
+int gnn_profile_last_iterations(float* elapsed_ms, int32_t* launches);
+
 #ifdef __cplusplus
 }
 #endif

@@ -25,6 +25,16 @@ import torch
 
 from . import graph_oracle as G
 
+# arithmetic type of the restatement: float32 as the reference; tests may switch to float64 to obtain a
+# rounding-free reference value when a float32-vs-float32 difference has to be attributed
+DTYPE = torch.float32
+
+
+def set_dtype(dtype) -> None:
+    global DTYPE
+    DTYPE = dtype
+
+
 SELU_ALPHA = 1.6732632423543772
 SELU_SCALE = 1.0507009873554805
 _M32 = 0xFFFFFFFF
@@ -95,7 +105,7 @@ class OracleMLP:
     @classmethod
     def from_weights(cls, weights: list, acts: list, drop=None, batchnorm: bool = False, requires_grad: bool = True):
         """ weights in Keras get_weights() order: [kernel, bias]*L (+ [gamma, beta, moving_mean, moving_var]) """
-        t = lambda a, g: torch.tensor(np.asarray(a), dtype=torch.float32).requires_grad_(g)
+        t = lambda a, g: torch.tensor(np.asarray(a), dtype=DTYPE).requires_grad_(g)
         L = len(acts)
         W = [t(weights[2 * i], requires_grad) for i in range(L)]
         b = [t(weights[2 * i + 1], requires_grad) for i in range(L)]
@@ -161,7 +171,7 @@ class OracleGraph:
         an_row, an_col, an_data = G.arcnode_coo(dst, n_nodes, aggregation_mode)
         ad_row, ad_col, ad_data = G.adjacency_coo(src, dst, an_data)
         if nodegraph is None: nodegraph = G.nodegraph(n_nodes, problem_based)
-        f = lambda a: torch.tensor(np.asarray(a), dtype=torch.float32)
+        f = lambda a: torch.tensor(np.asarray(a, dtype=np.float32), dtype=DTYPE)
         return cls(nodes=f(nodes), arcs=f(arcs), targets=f(targets), set_mask=torch.tensor(set_mask),
                    output_mask=torch.tensor(output_mask), sample_weights=f(sample_weights * np.ones(targets.shape[0])),
                    adj=G.transposed_row_major(ad_row, ad_col, ad_data, (n_nodes, n_nodes)),
@@ -173,12 +183,12 @@ def spmm(sp: dict, dense: torch.Tensor, fast: bool = False) -> torch.Tensor:
     """ tf.sparse.sparse_dense_matmul(sp, dense): rows accumulate their entries in stored (ascending) order """
     rows = torch.from_numpy(sp['indices'][:, 0])
     cols = torch.from_numpy(sp['indices'][:, 1])
-    vals = torch.from_numpy(sp['values'])
+    vals = torch.from_numpy(sp['values']).to(dense.dtype)
     if fast:   # multi-threaded CSR kernel, used only for the timed CPU baseline
         if '_csr' not in sp:
             sp['_csr'] = torch.sparse_csr_tensor(torch.from_numpy(sp['rowptr']), cols, vals, size=sp['dense_shape'])
         return sp['_csr'] @ dense
-    out = torch.zeros((sp['dense_shape'][0], dense.shape[1]), dtype=torch.float32)
+    out = torch.zeros((sp['dense_shape'][0], dense.shape[1]), dtype=dense.dtype)
     return out.index_add(0, rows, vals[:, None] * dense[cols])
 
 
@@ -205,9 +215,9 @@ def loop(g: OracleGraph, net_state: OracleMLP, net_output: OracleMLP, *, state_v
         labels = g.arcs[:, 2:]
     aggregated_arcs = spmm(g.arcnode, labels, fast_spmm)                                   # :259
     n_nodes = g.nodes.shape[0]
-    aggregated_nodes = torch.zeros((n_nodes, 0))                                         # :260
+    aggregated_nodes = torch.zeros((n_nodes, 0), dtype=DTYPE)                                         # :260
     if state_vect_dim > 0:
-        state = x0 if x0 is not None else 0.1 * torch.randn(n_nodes, state_vect_dim)    # :262
+        state = x0.to(DTYPE) if x0 is not None else 0.1 * torch.randn(n_nodes, state_vect_dim, dtype=DTYPE)    # :262
         aggregated_nodes = spmm(g.adj, g.nodes, fast_spmm)                               # :263
     else:
         state = g.nodes                                                                  # :265
