@@ -116,6 +116,7 @@ class BaseClass(ABC):
         grads = torch.autograd.grad(loss, flat, allow_unused=True)
         grads = [torch.zeros_like(v) if gr is None else gr for v, gr in zip(flat, grads)]
         if not isinstance(iters, list): iters = [iters]
+        distributed = getattr(self, 'distributed', False)
         pos, dW = 0, []
         for layer_idx, layer in enumerate(wS):
             for _ in layer:
@@ -123,6 +124,9 @@ class BaseClass(ABC):
                 pos += 1
         dW += grads[pos:]
         assert len(dW) == len(flat)
+        if distributed:   # graph batches sharded by whole graph over the ranks: one all-reduce of the flat gradient
+            from .dist_graph import allreduce_gradients
+            dW = allreduce_gradients(dW, getattr(self, 'process_group', None))
         self.optimizer.apply_gradients(zip(dW, flat))
         return iters, loss.detach()
 

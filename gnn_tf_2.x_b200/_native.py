@@ -50,7 +50,12 @@ class gnn_loop_args(C.Structure):
                 ('x0', C.c_void_p), ('nodes', C.c_void_p), ('agg_nodes', C.c_void_p), ('agg_arcs', C.c_void_p),
                 ('max_iter', C.c_int32), ('threshold', C.c_float), ('training', C.c_int32),
                 ('save_for_backward', C.c_int32), ('seed', C.c_uint32),
-                ('x_out', C.c_void_p), ('k_out', C.c_void_p)]
+                ('x_out', C.c_void_p), ('k_out', C.c_void_p),
+                ('n_global', C.c_int64), ('row_offset', C.c_int64), ('exchange', C.c_void_p), ('exchange_user', C.c_void_p)]
+
+
+# callback type of gnn_loop_args.exchange: (user, t, x_next_offset, go_next_offset)
+EXCHANGE_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int32, C.c_int64, C.c_int64)
 
 
 # every symbol include/gnn_b200.h declares (tests check that the library exports all of them)

@@ -57,14 +57,21 @@ static inline int next_pow2(int v) {
 #define SELU_ALPHA 1.6732632423543772f
 #define SELU_SCALE 1.0507009873554805f
 
+// Activations. exp / division use the hardware approximations (ex2.approx, rcp.approx: ~2 ulp): the ABSOLUTE error
+// stays near 1e-7, far inside the 1e-4 parity tolerance, and the element-wise pass stays a handful of instructions.
+// selu / elu follow TensorFlow's own formula exp(z) - 1.
 __device__ __forceinline__ float act_apply(int act, float z) {
     switch (act) {
         case GNN_ACT_RELU: return fmaxf(z, 0.f);
-        case GNN_ACT_TANH: return tanhf(z);
-        case GNN_ACT_SIGMOID: return 1.f / (1.f + expf(-z));
-        case GNN_ACT_SELU: return z > 0.f ? SELU_SCALE * z : (SELU_SCALE * SELU_ALPHA) * expm1f(z);
-        case GNN_ACT_ELU: return z > 0.f ? z : expm1f(z);
-        case GNN_ACT_SOFTPLUS: return z > 20.f ? z : log1pf(expf(z));
+        case GNN_ACT_TANH: {
+            const float a = fminf(fabsf(z), 15.f);          // tanh(15) == 1 in fp32
+            const float e = __expf(2.f * a);
+            return copysignf(1.f - __fdividef(2.f, e + 1.f), z);
+        }
+        case GNN_ACT_SIGMOID: return __fdividef(1.f, 1.f + __expf(-z));
+        case GNN_ACT_SELU: return z > 0.f ? SELU_SCALE * z : (SELU_SCALE * SELU_ALPHA) * (__expf(z) - 1.f);
+        case GNN_ACT_ELU: return z > 0.f ? z : __expf(z) - 1.f;
+        case GNN_ACT_SOFTPLUS: return z > 15.f ? z : __logf(1.f + __expf(z));
         default: return z;  // linear (softmax is handled row-wise by its caller)
     }
 }
@@ -107,6 +114,29 @@ __device__ __forceinline__ bool dropout_keep(uint32_t key, uint64_t idx, float r
 }
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+// L2 eviction policies: the gathered state rows are re-read ~degree times per iteration -> keep (evict_last);
+// everything that streams through once (new state, saved aggregates) -> evict_first
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ float4 ldg4_hint(const float* p, uint64_t pol) {
+    float4 v;
+    asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ void st4_hint(float* p, float4 v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;"
+                 :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
+}
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 

@@ -25,6 +25,7 @@ struct IterParams {
     const int32_t* col;
     const float* val;        // NULL => row scale in cst[:, C]
     long long N;
+    long long row_offset;    // global id of local row 0 (node-range partition; 0 on a single GPU)
     // state
     const float* x_in;       // [N, DP]
     float* x_out;            // [N, DP]  (pre-BN output h_t when bn_train)
@@ -159,13 +160,14 @@ __device__ __forceinline__ void gather_group(const float* __restrict__ x_in, con
             const float sc = sscale[i];
             acc.x *= sc; acc.y *= sc; acc.z *= sc; acc.w *= sc;
         }
-        if (agg_save && i < nvalid) st4(agg_save + (size_t)i * DP + 4 * lig, acc);
+        if (agg_save && i < nvalid) st4_hint(agg_save + (size_t)i * DP + 4 * lig, acc, l2_policy_evict_first());
         st4(tile_agg + i * SA + 4 * lig, acc);
         acc = make_float4(0.f, 0.f, 0.f, 0.f);
         ++i;
         next = srow[i + 1 <= i0 + NPG ? i + 1 : i0 + NPG];
     };
     const float* xl = x_in + 4 * lig;
+    const uint64_t keep = l2_policy_evict_last();
     while (e < eend) {
         int idx[GB];
         float w[GB];
@@ -177,7 +179,7 @@ __device__ __forceinline__ void gather_group(const float* __restrict__ x_in, con
             if (HAS_VAL) w[b] = STAGED ? vals[ee] : __ldg(vals + ee);
         }
 #pragma unroll
-        for (int b = 0; b < GB; ++b) r[b] = ldg4(xl + (size_t)idx[b] * DP);   // (2) GB loads in flight
+        for (int b = 0; b < GB; ++b) r[b] = ldg4_hint(xl + (size_t)idx[b] * DP, keep);   // (2) GB loads in flight
 #pragma unroll
         for (int b = 0; b < GB; ++b) {   // (3) stored-order accumulation
             const int ee = e + b;
@@ -253,7 +255,7 @@ __global__ void __launch_bounds__(NT, GNN_FWD_MIN_CTAS) state_iter_kernel(const 
         for (int item = tid; item < TN * LPN; item += NT) {
             const int i = item / LPN;
             float* dstp = bufA + i * SA + 4 * lig;
-            if (i < nvalid) cp_async16(dstp, p.x_in + (size_t)(n0 + i) * DP + 4 * lig);
+            if (i < nvalid) cp_async16(dstp, p.x_in + (size_t)(p.row_offset + n0 + i) * DP + 4 * lig);
             else st4(dstp, make_float4(0.f, 0.f, 0.f, 0.f));
         }
         for (int item = tid; item < TN * (CP / 4); item += NT) {
@@ -288,7 +290,7 @@ __global__ void __launch_bounds__(NT, GNN_FWD_MIN_CTAS) state_iter_kernel(const 
                 float* q = bufA + i * SA + 4 * c;
                 float4 v = ld4(q);
                 float* vv = reinterpret_cast<float*>(&v);
-                const uint64_t rbase = (uint64_t)(n0 + i) * (uint64_t)F_in;
+                const uint64_t rbase = (uint64_t)(p.row_offset + n0 + i) * (uint64_t)F_in;
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const int kc = keras_input_col(4 * c + u, D, DP, net.NL_self, net.NL_agg, net.AL);
@@ -356,7 +358,7 @@ __global__ void __launch_bounds__(NT, GNN_FWD_MIN_CTAS) state_iter_kernel(const 
                     for (int c = 0; c < 4; ++c) {
                         const int j = 4 * cg + c;
                         float y = act_apply(act, v[c]);
-                        if (drop_here) y = drop1(y, j < odim, key, (uint64_t)(n0 + row) * (uint64_t)odim + j, rate, dscale);
+                        if (drop_here) y = drop1(y, j < odim, key, (uint64_t)(p.row_offset + n0 + row) * (uint64_t)odim + j, rate, dscale);
                         if (affine) y = fmaf(aff_a[j], y, aff_c[j]);
                         v[c] = (j < odim) ? y : 0.f;
                     }
@@ -368,6 +370,7 @@ __global__ void __launch_bounds__(NT, GNN_FWD_MIN_CTAS) state_iter_kernel(const 
 
         // ---- 4. epilogue: store + convergence test --------------------------------------------------
         bool any_moving = false;
+        const uint64_t stream_pol = l2_policy_evict_first();
         for (int item = tid; item < TN * LPN; item += NT) {
             const int i = item / LPN;  // lig == item % LPN because NT % LPN == 0
             const long long n = n0 + i;
@@ -375,13 +378,13 @@ __global__ void __launch_bounds__(NT, GNN_FWD_MIN_CTAS) state_iter_kernel(const 
             float4 xn = ld4(bufA + i * SA + net.final_off + 4 * lig);
             float d2 = 0.f, o2 = 0.f;
             if (valid) {
-                st4(p.x_out + (size_t)n * DP + 4 * lig, xn);
+                st4_hint(p.x_out + (size_t)(p.row_offset + n) * DP + 4 * lig, xn, stream_pol);
                 if (p.bn_train) {
                     bn_s1[0] += xn.x; bn_s1[1] += xn.y; bn_s1[2] += xn.z; bn_s1[3] += xn.w;
                     bn_s2[0] += (double)xn.x * xn.x; bn_s2[1] += (double)xn.y * xn.y;
                     bn_s2[2] += (double)xn.z * xn.z; bn_s2[3] += (double)xn.w * xn.w;
                 } else {
-                    const float4 xo = drop_in ? ldg4(p.x_in + (size_t)n * DP + 4 * lig) : ld4(bufA + i * SA + 4 * lig);
+                    const float4 xo = drop_in ? ldg4(p.x_in + (size_t)(p.row_offset + n) * DP + 4 * lig) : ld4(bufA + i * SA + 4 * lig);
                     const float dx = xn.x - xo.x, dy = xn.y - xo.y, dz = xn.z - xo.z, dw = xn.w - xo.w;
                     d2 = dx * dx + dy * dy + dz * dz + dw * dw;
                     o2 = xo.x * xo.x + xo.y * xo.y + xo.z * xo.z + xo.w * xo.w;

@@ -108,13 +108,14 @@ int carve(const gnn_graph* g, const gnn_loop_args* a, const NetLayout& lay, void
     DeviceInfo di;
     GNN_TRY(device_info(&di));
     const size_t N = (size_t)g->n_nodes;
+    const size_t NG = a->n_global > 0 ? (size_t)a->n_global : N;   // rows of the (replicated) state buffers
     const bool bn_train = a->training && lay.has_bn;
     const bool save = a->save_for_backward != 0;
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes ? bytes : 4, 256); return o; };
     char* b = (char*)base;
     memset(w, 0, sizeof(*w));
-    w->slab = N * (size_t)lay.DP;
+    w->slab = NG * (size_t)lay.DP;
     w->max_ctas = di.sms * 32;
     w->x_slabs = save ? a->max_iter + 1 : 2;
     size_t o_ctl = take((size_t)(a->max_iter + 2) * sizeof(int));
@@ -153,6 +154,12 @@ int check_args(const gnn_graph* g, const gnn_mlp* net, const gnn_loop_args* a) {
     if (g->n_nodes > 0 && (!g->rowptr || (!g->col && g->n_arcs > 0))) GNN_FAIL(GNN_ERR_INVALID, "graph CSR missing");
     if (!g->val && !g->row_scale && g->n_arcs > 0) GNN_FAIL(GNN_ERR_INVALID, "graph needs val or row_scale");
     if (a->NL_self < 0 || a->NL_agg < 0 || a->AL < 0) GNN_FAIL(GNN_ERR_INVALID, "negative label width");
+    if (a->n_global > 0) {
+        if (a->row_offset < 0 || a->row_offset + g->n_nodes > a->n_global) GNN_FAIL(GNN_ERR_INVALID, "partition rows outside the graph");
+        if (a->training || a->save_for_backward) GNN_FAIL(GNN_ERR_UNSUPPORTED, "partitioned calls are forward-only");
+    } else if (a->row_offset != 0 || a->exchange) {
+        GNN_FAIL(GNN_ERR_INVALID, "row_offset / exchange need n_global");
+    }
     for (int l = 0; l <= net->n_layers && l <= GNN_MAX_LAYERS; ++l)
         if (net->drop_rate[l] > 0.f && a->training == 0) { /* inactive in inference */ }
     return GNN_OK;
@@ -235,6 +242,7 @@ extern "C" int gnn_state_loop_forward(const gnn_graph* g, const gnn_mlp* net, co
     GNN_TRY(carve(g, a, lay, workspace, &w));
     if (!workspace || workspace_bytes < w.total) GNN_FAIL(GNN_ERR_WORKSPACE, "workspace %zu < %zu bytes", workspace_bytes, w.total);
     const long long N = g->n_nodes;
+    const long long NGLOB = a->n_global > 0 ? a->n_global : N;
     const bool bn_train = a->training && lay.has_bn;
     const bool save = a->save_for_backward != 0;
     int* go = w.ctl;
@@ -248,20 +256,23 @@ extern "C" int gnn_state_loop_forward(const gnn_graph* g, const gnn_mlp* net, co
         pack_net_kernel<<<(lay.total_floats + 255) / 256, 256, 0, stream>>>(pp);
         GNN_LAUNCH_CHECK();
     }
-    if (N == 0) {
+    if (NGLOB == 0) {
         GNN_CUDA(cudaMemsetAsync(a->k_out, 0, sizeof(float), stream));
         return GNN_OK;
     }
-    pack_cst_kernel<<<(unsigned)ceil_div(N * lay.CP, 256), 256, 0, stream>>>(a->nodes, a->agg_nodes, a->agg_arcs,
-                                                                             plan.has_val ? nullptr : g->row_scale, N, lay.NL_self,
-                                                                             lay.NL_agg, lay.AL, lay.CP, w.cst);
-    GNN_LAUNCH_CHECK();
-    init_state_kernel<<<(unsigned)ceil_div(N, 128), 128, 0, stream>>>(a->x0, N, lay.D, lay.DP, a->threshold, a->max_iter, w.X, go);
+    if (N > 0) {
+        pack_cst_kernel<<<(unsigned)ceil_div(N * lay.CP, 256), 256, 0, stream>>>(a->nodes, a->agg_nodes, a->agg_arcs,
+                                                                                 plan.has_val ? nullptr : g->row_scale, N, lay.NL_self,
+                                                                                 lay.NL_agg, lay.AL, lay.CP, w.cst);
+        GNN_LAUNCH_CHECK();
+    }
+    // the initial state is replicated: every rank pads all rows and evaluates the first condition on all of them
+    init_state_kernel<<<(unsigned)ceil_div(NGLOB, 128), 128, 0, stream>>>(a->x0, NGLOB, lay.D, lay.DP, a->threshold, a->max_iter, w.X, go);
     GNN_LAUNCH_CHECK();
 
     IterParams p;
     memset(&p, 0, sizeof(p));
-    p.rowptr = g->rowptr; p.col = g->col; p.val = plan.has_val ? g->val : nullptr; p.N = N;
+    p.rowptr = g->rowptr; p.col = g->col; p.val = plan.has_val ? g->val : nullptr; p.N = N; p.row_offset = a->row_offset;
     p.cst = w.cst; p.wpack = w.wpack; p.k_ptr = kptr; p.thr = a->threshold; p.bn_partial = w.bn_partial;
     p.bn_train = bn_train; p.seed = a->seed; p.training = a->training; p.scol_cap = plan.scol_cap; p.net = lay;
     BnApplyKernel bn_apply = kernel_set(lay.DP)->bn_apply;
@@ -279,10 +290,15 @@ extern "C" int gnn_state_loop_forward(const gnn_graph* g, const gnn_mlp* net, co
         p.go_cur = go + t;
         p.go_next = (t + 1 < a->max_iter) ? go + t + 1 : nullptr;
         p.t = t;
-        void* args[] = {(void*)&p};
-        GNN_CUDA(cudaLaunchKernel((const void*)plan.kernel, dim3(plan.grid), dim3(plan.ts.nt), args, plan.smem, stream));
-        GNN_LAUNCH_CHECK();
-        if (g_profile.enabled) ++g_profile.launches;
+        if (N > 0) {
+            void* args[] = {(void*)&p};
+            GNN_CUDA(cudaLaunchKernel((const void*)plan.kernel, dim3(plan.grid), dim3(plan.ts.nt), args, plan.smem, stream));
+            GNN_LAUNCH_CHECK();
+            if (g_profile.enabled) ++g_profile.launches;
+        }
+        if (a->exchange)
+            a->exchange(a->exchange_user, t, (int64_t)((char*)x_next - (char*)workspace),
+                        p.go_next ? (int64_t)((char*)p.go_next - (char*)workspace) : (int64_t)-1);
         if (bn_train) {
             float* stats = w.stats + (size_t)t * 4 * lay.DP;
             bn_stats_kernel<<<(lay.DP + 31) / 32, 32, 0, stream>>>(go + t, w.bn_partial, plan.grid, lay.DP, lay.D, N, net->bn_gamma,
@@ -298,8 +314,8 @@ extern "C" int gnn_state_loop_forward(const gnn_graph* g, const gnn_mlp* net, co
         GNN_CUDA(cudaEventRecord(g_profile.end, stream));
         g_profile.pending = true;
     }
-    finalize_kernel<<<(unsigned)ceil_div(std::max<long long>(N * lay.D, 1), 256), 256, 0, stream>>>(
-        kptr, w.X, (long long)w.slab, save ? 0 : 2, N, lay.D, lay.DP, a->x_out, a->k_out);
+    finalize_kernel<<<(unsigned)ceil_div(std::max<long long>(NGLOB * lay.D, 1), 256), 256, 0, stream>>>(
+        kptr, w.X, (long long)w.slab, save ? 0 : 2, NGLOB, lay.D, lay.DP, a->x_out, a->k_out);
     GNN_LAUNCH_CHECK();
     return GNN_OK;
 }

@@ -1,6 +1,210 @@
 # coding=utf-8
-"""Multi-GPU execution of the state loop (placeholder until the partitioned path lands in this round)."""
+"""Multi-GPU execution (the reference itself is single-process).  One process per GPU,
+``torch.distributed`` (NCCL over NVLink/NVSwitch) for the plumbing.
+
+* **Batches of graphs** shard by whole graph: every rank runs the full loop on its own merged batch and the flat MLP
+  gradient is summed with one all-reduce per step (``allreduce_gradients``, used by ``BaseClass.training_step`` once
+  ``model.distributed = True``).  No data-path collective; iteration count and BatchNormalization statistics are those of
+  the rank's own batch (= the reference run on that shard).
+* **One giant graph** is split by contiguous node ranges (``GraphPartition``): rank r owns the destination rows
+  [lo_r, hi_r) of the CSR (global column ids) and the matching rows of the state; every rank keeps a full-size state
+  buffer.  After each iteration the ranks exchange the rows other ranks gather from (``HaloPlan``: all-gather when almost
+  everything is needed, all-to-all of the packed boundary rows otherwise) and max-reduce the convergence flag, all
+  enqueued on the compute stream by the library's ``exchange`` callback -- still no host synchronisation in the loop.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+import torch
+import torch.distributed as dist
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# graph batches: gradient all-reduce
+# ---------------------------------------------------------------------------------------------------------------------
+def allreduce_gradients(grads: list[torch.Tensor], group=None) -> list[torch.Tensor]:
+    """ SUM the gradients of all ranks with ONE collective over a flat buffer (the loss is a sum over targets,
+    GNN.py:199, so the gradient of the global batch is the sum of the per-shard gradients) """
+    if not dist.is_initialized() or dist.get_world_size(group) == 1: return grads
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    out, pos = [], 0
+    for g in grads:
+        out.append(flat[pos:pos + g.numel()].view_as(g))
+        pos += g.numel()
+    return out
+
+
+def shard_graphs(graphs: list, rank: int, world: int) -> list:
+    """ whole graphs per rank, contiguous blocks of (almost) equal length """
+    bounds = np.linspace(0, len(graphs), world + 1).astype(int)
+    return graphs[bounds[rank]:bounds[rank + 1]]
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# one giant graph: node-range partition
+# ---------------------------------------------------------------------------------------------------------------------
+def partition_bounds(n_nodes: int, world: int) -> list[int]:
+    """ contiguous node ranges of equal length (the last one takes the remainder) """
+    step = -(-n_nodes // world)
+    return [min(r * step, n_nodes) for r in range(world)] + [n_nodes]
+
+
+class HaloPlan:
+    """ which state rows a rank must receive from / send to every other rank after each iteration.
+    Device-agnostic (CUDA + NCCL in production, CPU + gloo in the tests). """
+
+    def __init__(self, cols: torch.Tensor, bounds: list[int], rank: int, world: int, group=None, allgather_threshold: float = 0.5):
+        self.rank, self.world, self.group, self.bounds = rank, world, group, bounds
+        lo, hi = bounds[rank], bounds[rank + 1]
+        device = cols.device
+        cols = cols.to(torch.int64)
+        needed = torch.unique(cols[(cols < lo) | (cols >= hi)])                     # sorted remote rows this rank gathers from
+        edges = torch.as_tensor(bounds[1:], dtype=torch.int64, device=device)
+        owner = torch.bucketize(needed, edges, right=True)
+        recv_counts = torch.bincount(owner, minlength=world)[:world]
+        send_counts = torch.empty_like(recv_counts)
+        dist.all_to_all_single(send_counts, recv_counts, group=group)
+        self.recv_counts, self.send_counts = recv_counts.tolist(), send_counts.tolist()
+        send_rows = torch.empty(int(sum(self.send_counts)), dtype=torch.int64, device=device)
+        dist.all_to_all_single(send_rows, needed, output_split_sizes=self.send_counts, input_split_sizes=self.recv_counts, group=group)
+        self.recv_rows, self.send_rows = needed, send_rows                          # global ids, grouped by peer rank
+        # all-gather instead of all-to-all when most remote rows are needed anyway (uniform-random graphs)
+        sizes = [bounds[r + 1] - bounds[r] for r in range(world)]
+        remote = bounds[-1] - (hi - lo)
+        frac = torch.tensor([needed.numel() / max(remote, 1)], device=device)
+        dist.all_reduce(frac, op=dist.ReduceOp.MAX, group=group)
+        self.use_allgather = bool(frac.item() > allgather_threshold) and len(set(sizes)) == 1
+        self.lo, self.hi = lo, hi
+
+    def exchange(self, x_full: torch.Tensor) -> None:
+        """ make the rows of x_full that this rank gathers from valid (its own rows [lo, hi) were just computed) """
+        if self.world == 1: return
+        if self.use_allgather:
+            dist.all_gather_into_tensor(x_full, x_full[self.lo:self.hi], group=self.group)
+            return
+        send = x_full.index_select(0, self.send_rows)
+        recv = torch.empty((self.recv_rows.numel(), x_full.shape[1]), dtype=x_full.dtype, device=x_full.device)
+        dist.all_to_all_single(recv, send, output_split_sizes=self.recv_counts, input_split_sizes=self.send_counts, group=self.group)
+        x_full.index_copy_(0, self.recv_rows, recv)
+
+    def bytes_received_per_exchange(self, row_bytes: int) -> int:
+        if self.use_allgather: return (self.bounds[-1] - (self.hi - self.lo)) * row_bytes
+        return int(self.recv_rows.numel()) * row_bytes
+
+
+class GraphPartition:
+    """ rows [lo, hi) of one GraphObject on this rank: local CSRs with global column ids + replicated labels.
+    Passed as ``partition=`` to ``state_loop`` (attributes n_global, row_offset, exchange). """
+
+    def __init__(self, g, rank: int, world: int, device=None, group=None):
+        from . import _native
+        from .graph_class import GraphObject
+        assert isinstance(g, GraphObject)
+        self.rank, self.world, self.group = rank, world, group
+        self.device = _native.default_device() if device is None else torch.device(device)
+        self.n_global = int(g.nodes.shape[0])
+        self.bounds = partition_bounds(self.n_global, world)
+        lo, hi = self.bounds[rank], self.bounds[rank + 1]
+        self.row_offset, self.n_local = lo, hi - lo
+        adj, an = g.Adjacency, g.ArcNode                          # COO: Adjacency (src, dst), ArcNode (arc, dst)
+        mine = np.nonzero((adj.col >= lo) & (adj.col < hi))[0]    # arcs entering my nodes, in arc order
+        dev = self.device
+        i32 = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.int32), device=dev)
+        f32 = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.float32), device=dev)
+        # Adjacency^T rows = local destination, columns = GLOBAL source; ArcNode^T rows = local destination, columns =
+        # position of the arc among this rank's arcs (its labels are kept in that order)
+        self.Adjacency = _native.csr_build(i32(adj.col[mine] - lo), i32(adj.row[mine]), f32(adj.data[mine]), self.n_local, self.n_global)
+        self.ArcNode = _native.csr_build(i32(an.col[mine] - lo), i32(np.arange(len(mine))), f32(an.data[mine]), self.n_local, max(len(mine), 1))
+        self.arc_labels = f32(g.arcs[mine, 2:])
+        self.nodes = f32(g.nodes)                                 # replicated (label widths are small)
+        self.n_arcs_local = int(len(mine))
+        self.halo = HaloPlan(self.Adjacency.col, self.bounds, rank, world, group) if world > 1 else None
+
+    def exchange(self, t: int, x_full: torch.Tensor, go_flag: Optional[torch.Tensor]) -> None:
+        if self.world == 1: return
+        self.halo.exchange(x_full)
+        if go_flag is not None: dist.all_reduce(go_flag, op=dist.ReduceOp.MAX, group=self.group)
+
+
+def partitioned_loop(gnn, part: GraphPartition, x0: Optional[torch.Tensor] = None, seed: int = 0):
+    """ GNNnodeBased.Loop (inference) on one node range; returns (k, full state [n_global, D], outputs of the LOCAL rows).
+    Same arithmetic as the single-GPU call: the result does not depend on the number of ranks. """
+    from .state_loop import state_loop, sparse_dense
+    gnn.to(part.device)
+    lo, hi = part.row_offset, part.row_offset + part.n_local
+    with torch.no_grad():
+        aggregated_arcs = sparse_dense(part.ArcNode, part.arc_labels)
+        if gnn.state_vect_dim > 0:
+            state0 = x0 if x0 is not None else gnn.initial_state
+            if state0 is None: raise ValueError('a partitioned loop needs a replicated initial state (x0 or gnn.initial_state)')
+            state0 = state0.to(part.device, torch.float32)
+            aggregated_nodes = sparse_dense(part.Adjacency, part.nodes)
+            node_self = part.nodes[lo:hi].contiguous()
+        else:
+            state0 = part.nodes
+            aggregated_nodes = torch.zeros((part.n_local, 0), dtype=torch.float32, device=part.device)
+            node_self = None
+        k, state = state_loop(part.Adjacency, gnn.net_state, state0, node_self, aggregated_nodes, aggregated_arcs,
+                              max_iteration=gnn.max_iteration, threshold=gnn.state_threshold, training=False, seed=seed, partition=part)
+        local = state[lo:hi]
+        net_in = torch.cat([local, part.nodes[lo:hi]], dim=1) if gnn.state_vect_dim else local
+        out = gnn.net_output(net_in, training=False)
+    return k, state, out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# bench.py leg for N > 1 (strong scaling of the C4 graph)
+# ---------------------------------------------------------------------------------------------------------------------
 def bench_partitioned(g_host, wl, build_gnn, args, device, rank, world):
-    raise NotImplementedError('node-range partitioned execution is not implemented yet')
+    from . import _native
+    gnn = build_gnn()
+    part = GraphPartition(g_host, rank, world, device=device)
+    E = wl['E']
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup): fn()
+        torch.cuda.synchronize(); dist.barrier()
+        start.record()
+        for _ in range(steps): fn()
+        stop.record()
+        torch.cuda.synchronize(); dist.barrier()
+        ms = torch.tensor([start.elapsed_time(stop) / steps], device=device)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)       # the job is as slow as its slowest rank
+        return float(ms.item())
+
+    ks = []
+
+    def fwd():
+        k, state, out = partitioned_loop(gnn, part)
+        ks.append(k)
+
+    _native.launch_count(reset=True)
+    warm = max(3, args.warmup)
+    ms_fwd = timed(fwd, args.steps, warm)
+    launches = _native.launch_count() * args.steps // (args.steps + warm)
+    k_fwd = float(ks[-1])
+
+    # e2e: host buffers of the local rows -> device (CSR build included) -> loop -> local outputs back on the host
+    g_host.pin_host_buffers()
+    x0_host = torch.from_numpy(wl['x0']).pin_memory()
+    held = []
+
+    def e2e_step():
+        gnn.initial_state = x0_host.to(device, non_blocking=True)
+        p = GraphPartition(g_host, rank, world, device=device)
+        k, state, out = partitioned_loop(gnn, p)
+        held.append(out.cpu())
+        if len(held) > 2: held.pop(0)
+
+    ms_e2e = timed(e2e_step, max(1, args.steps // 2), 1)
+    local_bytes = part.n_arcs_local * (4 * 6 + 4 * wl['AL']) + g_host.nodes.nbytes + x0_host.numel() * 4
+    halo = part.halo.bytes_received_per_exchange(128) if part.halo is not None else 0
+    return {'value': E * k_fwd / (ms_fwd * 1e-3), 'ms_per_step': ms_fwd, 'iterations': k_fwd, 'gpu_launches': int(launches),
+            'e2e': {'value': E * k_fwd / (ms_e2e * 1e-3), 'unit': 'arc-updates/s', 'ms_per_step': ms_e2e,
+                    'h2d_bytes_per_step': int(local_bytes), 'd2h_bytes_per_step': int(held[-1].numel() * 4)},
+            'partition': {'ranks': world, 'rows_per_rank': part.n_local, 'exchange': 'all_gather' if part.halo.use_allgather else 'all_to_all',
+                          'halo_bytes_received_per_iteration_per_rank': int(halo)}}

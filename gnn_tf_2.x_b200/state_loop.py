@@ -45,7 +45,7 @@ def sparse_dense(sp: SparseCSR, dense: torch.Tensor) -> torch.Tensor:
 
 
 class _LoopConfig:
-    __slots__ = ('adj', 'net', 'spec', 'D', 'NL_self', 'NL_agg', 'AL', 'max_iter', 'threshold', 'training', 'seed', 'save')
+    __slots__ = ('adj', 'net', 'spec', 'D', 'NL_self', 'NL_agg', 'AL', 'max_iter', 'threshold', 'training', 'seed', 'save', 'partition')
 
 
 class _StateLoop(torch.autograd.Function):
@@ -54,11 +54,12 @@ class _StateLoop(torch.autograd.Function):
     def forward(ctx, cfg: _LoopConfig, x0, nodes, agg_nodes, agg_arcs, *params):
         lib = N.lib()
         device = x0.device
-        n_nodes = int(x0.shape[0])
+        n_nodes = int(x0.shape[0])   # rows of the state: all nodes of the graph (also when partitioned)
         x0c = x0.detach().contiguous()
         nodes_c = None if nodes is None else nodes.detach().contiguous()
         agg_nodes_c, agg_arcs_c = agg_nodes.detach().contiguous(), agg_arcs.detach().contiguous()
         save = cfg.save   # decided by the caller: grad mode is always off inside Function.forward
+        part = cfg.partition
 
         keep = []
         mlp = N.make_mlp(cfg.spec, keep)
@@ -73,13 +74,33 @@ class _StateLoop(torch.autograd.Function):
         args.training, args.save_for_backward, args.seed = int(bool(cfg.training)), int(save), int(cfg.seed) & 0xFFFFFFFF
         args.x_out, args.k_out = x_out.data_ptr(), k_out.data_ptr()
 
+        if part is not None:
+            args.n_global, args.row_offset = int(part.n_global), int(part.row_offset)
         nbytes = C.c_size_t(0)
         N.check(lib.gnn_state_loop_workspace_bytes(C.byref(graph), C.byref(mlp), C.byref(args), C.byref(nbytes)),
                 'gnn_state_loop_workspace_bytes')
         workspace = torch.empty(nbytes.value, dtype=torch.uint8, device=device)
+        callback, failure = None, []
+        if part is not None:
+            DP = 4
+            while DP < cfg.D: DP *= 2
+            slab_bytes = int(part.n_global) * DP * 4
+
+            def _exchange(_user, t, x_off, go_off):
+                # called by the library between the enqueues of two iterations: enqueue the collectives on the same stream
+                try:
+                    x_full = workspace[x_off:x_off + slab_bytes].view(torch.float32).view(int(part.n_global), DP)
+                    go = None if go_off < 0 else workspace[go_off:go_off + 4].view(torch.int32)
+                    part.exchange(int(t), x_full, go)
+                except BaseException as exc:   # never let an exception cross the C boundary
+                    failure.append(exc)
+
+            callback = N.EXCHANGE_FN(_exchange)
+            args.exchange = C.cast(callback, C.c_void_p)
         with torch.cuda.device(device):
             N.check(lib.gnn_state_loop_forward(C.byref(graph), C.byref(mlp), C.byref(args), workspace.data_ptr(), nbytes.value,
                                                N._stream(device)), 'gnn_state_loop_forward')
+        if failure: raise failure[0]
         if save:
             ctx.cfg, ctx.workspace, ctx.nbytes = cfg, workspace, nbytes.value
             ctx.held = (x0c, nodes_c, agg_nodes_c, agg_arcs_c, x_out, k_out, keep)
@@ -145,8 +166,12 @@ class _StateLoop(torch.autograd.Function):
 
 def state_loop(adjacency: SparseCSR, net_state: Sequential, x0: torch.Tensor, nodes: Optional[torch.Tensor],
                aggregated_nodes: torch.Tensor, aggregated_arcs: torch.Tensor, *, max_iteration: int, threshold: float,
-               training: bool, seed: int = 0):
+               training: bool, seed: int = 0, partition=None):
     """ run the whole state-convergence loop on the device.
+
+    :param partition: None, or an object with ``n_global``, ``row_offset`` and ``exchange(t, x_full, go_flag)`` for one
+        node range of a graph split over several GPUs (``dist_graph.GraphPartition``): ``adjacency`` then holds the local
+        rows with GLOBAL column ids, ``x0`` is the full (replicated) initial state, labels are local rows; forward only.
 
     :param adjacency: Adjacency^T as SparseCSR (rows = destination), with the transposed structure when gradients are needed
     :param net_state: keras_compat.Sequential; its parameters receive gradients through autograd
@@ -162,6 +187,7 @@ def state_loop(adjacency: SparseCSR, net_state: Sequential, x0: torch.Tensor, no
     cfg.NL_self = 0 if nodes is None else int(nodes.shape[1])
     cfg.NL_agg, cfg.AL = int(aggregated_nodes.shape[1]), int(aggregated_arcs.shape[1])
     cfg.max_iter, cfg.threshold, cfg.training, cfg.seed = int(max_iteration), float(threshold), bool(training), int(seed)
+    cfg.partition = partition
     if cfg.spec.dims[0] != 2 * cfg.D + cfg.NL_self + cfg.NL_agg + cfg.AL:
         raise ValueError(f'net_state input width {cfg.spec.dims[0]} does not match the graph: expected '
                          f'{2 * cfg.D + cfg.NL_self + cfg.NL_agg + cfg.AL} = AL + 2*(NL + state_vect_dim)')
@@ -170,5 +196,7 @@ def state_loop(adjacency: SparseCSR, net_state: Sequential, x0: torch.Tensor, no
     params = net_state.trainable_variables
     cfg.save = bool(torch.is_grad_enabled() and any(t is not None and t.requires_grad
                                                     for t in [x0, nodes, aggregated_nodes, aggregated_arcs] + list(params)))
+    if partition is not None and (cfg.save or training):
+        raise NotImplementedError('a partitioned state loop is forward-only: call it under torch.no_grad() with training=False')
     x, k = _StateLoop.apply(cfg, x0.to(torch.float32), nodes, aggregated_nodes, aggregated_arcs, *params)
     return k, x

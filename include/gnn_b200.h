@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define GNN_B200_ABI_VERSION 1
+#define GNN_B200_ABI_VERSION 2
 #define GNN_MAX_LAYERS 4 /* Dense layers per MLP */
 
 enum gnn_error {
@@ -142,8 +142,21 @@ typedef struct gnn_loop_args {
     int32_t training;         /* Keras `training` flag: dropout active, BatchNormalization uses batch statistics */
     int32_t save_for_backward;/* keep the iterates in the workspace so that gnn_state_loop_backward can run */
     uint32_t seed;            /* dropout generator seed of this call */
-    float* x_out;             /* device [N, D] converged state */
+    float* x_out;             /* device [N, D] converged state ([n_global, D] when partitioned) */
     float* k_out;             /* device [1] number of iterations, float32 as GNN.py:267 */
+    /* Node-range partition of one graph over several GPUs (all zero / NULL on a single GPU).  The graph handed to the
+     * call holds the rows (destination nodes) [row_offset, row_offset + g->n_nodes) of a graph with n_global nodes;
+     * its column indices are GLOBAL node ids.  x0 and x_out are full [n_global, D] arrays (replicated), nodes /
+     * agg_nodes / agg_arcs hold the local rows only.  After the kernels of iteration t have been enqueued the library
+     * calls exchange(user, t, x_next_offset, go_next_offset): byte offsets INTO THE WORKSPACE of the full state buffer
+     * [n_global, DP] whose local rows were just written and of the int32 flag of iteration t+1 (-1 after the last
+     * iteration).  The callback enqueues, on the same stream, the exchange of the boundary rows and the max-reduction
+     * of the flag (e.g. NCCL through torch.distributed), so that every rank runs the same number of iterations.
+     * Partitioned calls are forward-only (training = 0, save_for_backward = 0). */
+    int64_t n_global;
+    int64_t row_offset;
+    void (*exchange)(void* user, int32_t t, int64_t x_next_offset, int64_t go_next_offset);
+    void* exchange_user;
 } gnn_loop_args;
 
 int gnn_state_loop_workspace_bytes(const gnn_graph* g, const gnn_mlp* net, const gnn_loop_args* a, size_t* bytes);

@@ -243,3 +243,61 @@ def test_label_gradients_for_lgnn():
     assert rel_err(g_nodes.cpu().numpy(), w_nodes.numpy()) < TOL
     assert rel_err(g_labels.cpu().numpy(), w_labels.numpy()) < TOL
     assert rel_err(g_x0.cpu().numpy(), w_x0.numpy()) < TOL
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# node-range partition (multi-GPU path) on one GPU
+# ---------------------------------------------------------------------------------------------------------------------
+class _FakePartition:
+    """ rows [lo, hi) of a graph, no peers: what dist_graph.GraphPartition hands to state_loop """
+
+    def __init__(self, n_global, lo, calls):
+        self.n_global, self.row_offset, self.calls = n_global, lo, calls
+
+    def exchange(self, t, x_full, go_flag):
+        self.calls.append((t, tuple(x_full.shape), None if go_flag is None else int(go_flag.numel())))
+
+
+def test_partition_emulated_ranks_match_single_gpu():
+    """ three 'ranks' advance in lock step, one iteration at a time, each computing only its own node range from the
+    full previous state; the assembled trajectory must equal the single-GPU loop (same kernels, row_offset mechanics) """
+    _require_gpu()
+    from gnn_b200 import _native, dist_graph
+    from gnn_b200.state_loop import state_loop, sparse_dense
+    T = 4
+    case = random_case(seed=500, n_nodes=3000, n_arcs=24000, NL=3, AL=2, DS=8, act='tanh', max_iter=T, threshold=0.0, masks=False)
+    g, gt, gnn = build_product(case)
+    with torch.no_grad():
+        k_ref, x_ref, _ = gnn.Loop(gt, training=False)
+    assert float(k_ref) == T
+    n = 3000
+    bounds = dist_graph.partition_bounds(n, 3)
+    parts = [dist_graph.GraphPartition(g, r, 3, device='cuda') if False else None for r in range(3)]   # needs a process group: build by hand
+    x = torch.as_tensor(case['x0'], device='cuda')
+    adj, an = g.Adjacency, g.ArcNode
+    local = []
+    for r in range(3):
+        lo, hi = bounds[r], bounds[r + 1]
+        mine = np.nonzero((adj.col >= lo) & (adj.col < hi))[0]
+        i32 = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.int32), device='cuda')
+        f32 = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.float32), device='cuda')
+        A = _native.csr_build(i32(adj.col[mine] - lo), i32(adj.row[mine]), f32(adj.data[mine]), hi - lo, n)
+        AN = _native.csr_build(i32(an.col[mine] - lo), i32(np.arange(len(mine))), f32(an.data[mine]), hi - lo, max(len(mine), 1))
+        labels = f32(g.arcs[mine, 2:])
+        with torch.no_grad():
+            local.append((lo, hi, A, sparse_dense(AN, labels), sparse_dense(A, gt.nodes), gt.nodes[lo:hi].contiguous()))
+    calls = []
+    for t in range(T):
+        nxt = torch.empty_like(x)
+        for lo, hi, A, agg_arcs, agg_nodes, nodes_self in local:
+            with torch.no_grad():
+                k, full = state_loop(A, gnn.net_state, x, nodes_self, agg_nodes, agg_arcs, max_iteration=1, threshold=0.0, training=False,
+                                     partition=_FakePartition(n, lo, calls))
+            assert float(k) == 1.0
+            nxt[lo:hi] = full[lo:hi]
+        x = nxt
+    assert rel_err(x.cpu().numpy(), x_ref.cpu().numpy()) < 1e-6
+    assert calls[0] == (0, (n, 8), None)       # one exchange call per iteration; no next flag after the last iteration
+    with pytest.raises(NotImplementedError):
+        state_loop(local[0][2], gnn.net_state, x, local[0][5], local[0][4], local[0][3], max_iteration=1, threshold=0.0, training=True,
+                   partition=_FakePartition(n, 0, calls))
