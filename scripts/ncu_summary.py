@@ -30,7 +30,11 @@ for d in rows[2:]:
 src = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv'], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
 if len(rows) > 2:
-    hdr, data = rows[1], rows[2:]
+    hdr = rows[1]
+    data = []
+    for r in rows[2:]:
+        if len(r) != len(hdr) or r[0] == 'Address': break   # first captured launch only
+        data.append(r)
     isamp, iex, isrc = hdr.index('# Samples'), hdr.index('Instructions Executed'), hdr.index('Source')
     names = [h for h in hdr if h.startswith('stall_') and 'Not Issued' not in h]
     tot = sum(int(r[isamp]) for r in data) or 1
