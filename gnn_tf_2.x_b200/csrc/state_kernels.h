@@ -4,6 +4,7 @@
 #include "state_aux.cuh"
 #include "state_bwd.cuh"
 #include "state_fwd.cuh"
+#include "state_fwd_ws.cuh"
 
 namespace gnn {
 
@@ -15,6 +16,7 @@ typedef void (*BnBwdReduceKernel)(const int*, int, const float*, const float*, c
 
 struct KernelSet {
     IterKernel iter[2][2];      // [tile: 0 = 128 nodes x 128 threads, 1 = 32 x 32][has_val]
+    IterKernel iter_ws[2];      // warp-specialised pipeline [has_val]; NULL when the width is not covered
     BwdNodeKernel bwd_node[2];  // [tile: 0 = 64 nodes x 128 threads, 1 = 32 x 32]
     ScatterKernel scatter[2];   // [has_val]
     BnApplyKernel bn_apply;

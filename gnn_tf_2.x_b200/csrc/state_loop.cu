@@ -166,6 +166,7 @@ int check_args(const gnn_graph* g, const gnn_mlp* net, const gnn_loop_args* a) {
 }
 
 struct Plan {
+    bool ws;          // warp-specialised pipelined kernel
     NetLayout lay;
     TileShape ts;
     IterKernel kernel;
@@ -175,6 +176,17 @@ struct Plan {
     bool has_val;
 };
 
+// the warp-specialised kernel covers: one Dense layer, padded state width 16..32, no active dropout, enough tiles
+bool ws_applicable(const gnn_graph* g, const gnn_loop_args* a, const NetLayout& lay, int sms) {
+    const char* env = getenv("GNN_B200_KERNEL");
+    if (env && !strcmp(env, "sym")) return false;
+    if (lay.L != 1 || lay.DP < 16 || lay.DP > 32) return false;
+    if (a->training)
+        for (int i = 0; i <= lay.L; ++i) if (lay.drop[i] > 0.f) return false;
+    if (env && !strcmp(env, "ws")) return true;
+    return (g->n_nodes + WS_TN - 1) / WS_TN >= 2LL * sms;
+}
+
 int make_plan(const gnn_graph* g, const gnn_mlp* net, const gnn_loop_args* a, Plan* plan) {
     DeviceInfo di;
     GNN_TRY(device_info(&di));
@@ -183,7 +195,29 @@ int make_plan(const gnn_graph* g, const gnn_mlp* net, const gnn_loop_args* a, Pl
     const NetLayout& lay = plan->lay;
     plan->has_val = g->val != nullptr && g->row_scale == nullptr;
     const KernelSet* ks = kernel_set(lay.DP);
-    plan->kernel = ks ? ks->iter[plan->ts.tn == 128 ? 0 : 1][plan->has_val ? 1 : 0] : nullptr;
+    if (!ks) GNN_FAIL(GNN_ERR_UNSUPPORTED, "no kernel for padded state width %d", lay.DP);
+    plan->ws = false;
+
+    if (ws_applicable(g, a, lay, di.sms) && ks->iter_ws[plan->has_val ? 1 : 0]) {
+        // landing capacity: the average tile + 25 %, bounded by what one CTA per SM can hold
+        const long long avg = g->n_nodes > 0 ? (g->n_arcs * WS_TN) / g->n_nodes : 0;
+        int cap = (int)std::min<long long>(4096, std::max<long long>(64, (avg * 5 / 4 + 15) / 16 * 16));
+        while (cap > 16 && ws_smem_bytes(lay, cap, plan->has_val) + 4096 > (size_t)di.smem_optin) cap -= 16;
+        if (ws_smem_bytes(lay, cap, plan->has_val) + 4096 <= (size_t)di.smem_optin) {
+            plan->ws = true;
+            plan->kernel = ks->iter_ws[plan->has_val ? 1 : 0];
+            plan->ts = TileShape{WS_TN, WS_THREADS};
+            plan->scol_cap = cap;
+            plan->smem = ws_smem_bytes(lay, cap, plan->has_val);
+            int occ = 0;
+            GNN_TRY(kernel_occupancy((const void*)plan->kernel, WS_THREADS, plan->smem, &occ));
+            const long long ntiles = (g->n_nodes + WS_TN - 1) / WS_TN;
+            plan->grid = (int)std::max<long long>(1, std::min<long long>(ntiles, (long long)occ * di.sms));
+            return GNN_OK;
+        }
+    }
+
+    plan->kernel = ks->iter[plan->ts.tn == 128 ? 0 : 1][plan->has_val ? 1 : 0];
     if (!plan->kernel) GNN_FAIL(GNN_ERR_UNSUPPORTED, "no kernel for padded state width %d", lay.DP);
     const int TN = plan->ts.tn;
     const size_t fixed = ((size_t)lay.fwd_floats + (size_t)TN * lay.SA + (size_t)TN * lay.SB + ((TN + 1 + 3) & ~3)) * 4;

@@ -301,3 +301,39 @@ def test_partition_emulated_ranks_match_single_gpu():
     with pytest.raises(NotImplementedError):
         state_loop(local[0][2], gnn.net_state, x, local[0][5], local[0][4], local[0][3], max_iteration=1, threshold=0.0, training=True,
                    partition=_FakePartition(n, 0, calls))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# warp-specialised pipelined kernel (state_fwd_ws.cuh), forced on small cases too
+# ---------------------------------------------------------------------------------------------------------------------
+WS_CASES = {
+    'dp32_rowscale': dict(n_nodes=5000, n_arcs=50000, NL=3, AL=1, DS=32, act='selu', max_iter=7, threshold=0.0, bn=True),
+    'dp32_perarc': dict(n_nodes=3000, n_arcs=20000, NL=3, AL=2, DS=24, act='tanh', max_iter=6, custom_arcnode=True),
+    'dp16_ds0': dict(n_nodes=4000, n_arcs=9000, NL=14, AL=3, DS=0, act='selu', max_iter=5),
+    'dp8': dict(n_nodes=1000, n_arcs=6000, NL=5, AL=1, DS=0, act='sigmoid', max_iter=6),
+    'tiny_partial_tile': dict(n_nodes=70, n_arcs=900, NL=3, AL=1, DS=16, act='tanh', max_iter=5),
+    'hub_node_overflow': dict(n_nodes=600, n_arcs=30000, NL=3, AL=1, DS=32, act='tanh', max_iter=4, aggregation='average'),
+    'converging': dict(n_nodes=2000, n_arcs=10000, NL=3, AL=1, DS=8, act='linear', max_iter=60, threshold=0.01, weight_scale=0.05),
+}
+
+
+@pytest.mark.parametrize('name', sorted(WS_CASES))
+def test_ws_kernel_forward_and_training(name, monkeypatch):
+    _require_gpu()
+    monkeypatch.setenv('GNN_B200_KERNEL', 'ws')
+    case = random_case(seed=700 + sorted(WS_CASES).index(name), **WS_CASES[name])
+    assert_parity(run_cuda(case, training=False), run_oracle(case, training=False))
+    got, want = run_cuda(case, training=True), run_oracle(case, training=True)
+    assert_parity(got, want, want64=lambda: run_oracle(case, training=True, float64=True))
+
+
+def test_ws_and_symmetric_kernels_agree_bitwise(monkeypatch):
+    """ both kernels sum the arcs in stored order and use the same FMA order per output: identical states """
+    _require_gpu()
+    case = random_case(seed=710, n_nodes=30000, n_arcs=240000, NL=3, AL=1, DS=32, act='selu', max_iter=5, threshold=0.0, bn=True)
+    monkeypatch.setenv('GNN_B200_KERNEL', 'ws')
+    a = run_cuda(case, training=False)
+    monkeypatch.setenv('GNN_B200_KERNEL', 'sym')
+    b = run_cuda(case, training=False)
+    assert a['k'] == b['k']
+    assert rel_err(a['state'], b['state']) < 1e-6
