@@ -151,24 +151,6 @@ __global__ void __launch_bounds__(WS_THREADS, 1) state_iter_ws_kernel(const Iter
                 if (r + 3 < ecount) cp_async16_hint(lb + (size_t)(r + 3) * DP, xl + (size_t)s4.w * DP, keep);
             }
         };
-        // own state rows and constant rows -> tile b (asynchronous)
-        auto issue_own = [&](long long tile, int b) {
-            const long long n0 = tile * TN;
-            const int nvalid = (int)min((long long)TN, p.N - n0);
-            float* tb = tile0 + (size_t)b * TN * SA;
-            for (int item = gt; item < TN * LPN; item += WS_GATHER) {
-                const int i = item / LPN;
-                float* dstp = tb + i * SA + 4 * lig;
-                if (i < nvalid) cp_async16(dstp, p.x_in + (size_t)(p.row_offset + n0 + i) * DP + 4 * lig);
-                else st4(dstp, make_float4(0.f, 0.f, 0.f, 0.f));
-            }
-            for (int item = gt; item < TN * (CP / 4); item += WS_GATHER) {
-                const int i = item / (CP / 4), c = item % (CP / 4);
-                float* dstp = tb + i * SA + 2 * DP + 4 * c;
-                if (i < nvalid) cp_async16(dstp, p.cst + (size_t)(n0 + i) * CP + 4 * c);
-                else st4(dstp, make_float4(0.f, 0.f, 0.f, 0.f));
-            }
-        };
         // segment sums of this lane group's NPG nodes out of the landing zone, stored order
         auto consume = [&](long long tile, int q4, int q3, int b) {
             const long long n0 = tile * TN;
@@ -208,11 +190,12 @@ __global__ void __launch_bounds__(WS_THREADS, 1) state_iter_ws_kernel(const Iter
 
         // Pipeline (the gather warps run one tile ahead of the MLP warps; nothing they wait for is on the critical path):
         //   iteration it : rows(it+1) -> landing[b^1] and row pointers(it+3) -> srow        [asynchronous, group X_it]
-        //                  wait X_{it-1}, O_{it-1}: rows(it), own(it), row pointers(it+2) have landed
-        //                  arc sources(it+2) -> registers (latency overlaps consume) ; consume(it) -> tile[b] ; FULL[b]
-        //                  arc sources(it+2) -> scol ; wait EMPTY[b^1] (MLP done with tile it-1) ; own(it+1) -> tile[b^1] [O_it]
+        //                  wait X_{it-1}: rows(it) and row pointers(it+2) have landed
+        //                  arc sources(it+2) -> registers (latency overlaps consume)
+        //                  wait EMPTY[b] (MLP group b finished tile it-2, long ago) ; consume(it) -> tile[b] ; FULL[b]
+        //                  arc sources(it+2) -> scol
+        // (own state rows and constant rows are fetched by the MLP group that owns the tile buffer)
         auto tile_at = [&](int seq) { return first + (long long)seq * stride; };
-        // prologue: row pointers of tiles 0..2, arc sources of tiles 0..1, rows + own rows of tile 0
         for (int sq = 0; sq < 3; ++sq)
             if (tile_at(sq) < ntiles) stage_rowptr_async(tile_at(sq), sq);
         cp_async_commit();
@@ -221,28 +204,24 @@ __global__ void __launch_bounds__(WS_THREADS, 1) state_iter_ws_kernel(const Iter
         for (int sq = 0; sq < 2; ++sq)
             if (tile_at(sq) < ntiles) { load_cols(sq); store_cols(sq, sq); }
         named_bar_sync(GNN_BAR_GATHER, WS_GATHER);
-        if (first < ntiles) { issue_rows(0, 0, 0); issue_own(first, 0); }
-        cp_async_commit();   // plays the role of X_{-1} / O_{-1}
+        if (first < ntiles) issue_rows(0, 0, 0);
+        cp_async_commit();   // plays the role of X_{-1}
         int it = 0;
         for (long long tile = first; tile < ntiles; tile += stride, ++it) {
             const int b = it & 1;
             const long long t1 = tile + stride, t2 = tile + 2 * stride, t3 = tile + 3 * stride;
-            named_bar_sync(GNN_BAR_GATHER, WS_GATHER);       // consume(it-1) and store_cols(it+1) are done in every gather thread
+            named_bar_sync(GNN_BAR_GATHER, WS_GATHER);     // consume(it-1) and store_cols(it+1) are done in every gather thread
             if (t1 < ntiles) issue_rows((it + 1) & 3, (it + 1) % 3, b ^ 1);
             if (t3 < ntiles) stage_rowptr_async(t3, (it + 3) & 3);
             cp_async_commit();                             // X_it
             cp_async_wait_group<1>();                      // everything older than X_it has landed
-            named_bar_sync(GNN_BAR_GATHER, WS_GATHER);       // ... for every gather thread
+            named_bar_sync(GNN_BAR_GATHER, WS_GATHER);     // ... for every gather thread
             if (t2 < ntiles) load_cols((it + 2) & 3);
+            if (it >= 2) named_bar_sync(GNN_BAR_EMPTY0 + b, WS_PAIR);   // MLP group b is done with tile it-2
             consume(tile, it & 3, it % 3, b);
             __threadfence_block();
             named_bar_arrive(GNN_BAR_FULL0 + b, WS_PAIR);
             if (t2 < ntiles) store_cols((it + 2) & 3, (it + 2) % 3);
-            if (t1 < ntiles) {
-                if (it >= 1) named_bar_sync(GNN_BAR_EMPTY0 + (b ^ 1), WS_PAIR);   // MLP warps are done with tile it-1
-                issue_own(t1, b ^ 1);
-            }
-            cp_async_commit();                             // O_it
         }
         cp_async_wait_group<0>();
     } else {
@@ -263,13 +242,36 @@ __global__ void __launch_bounds__(WS_THREADS, 1) state_iter_ws_kernel(const Iter
         double bn_s1[4] = {0., 0., 0., 0.}, bn_s2[4] = {0., 0., 0., 0.};
         bool any_moving = false;
 
+        // own state rows and constant rows of a tile -> this group's tile buffer (asynchronous; the gather warps only
+        // write the aggregate columns, so the two never touch the same bytes)
+        float* tb = tile0 + (size_t)mgroup * TN * SA;
+        auto issue_own = [&](long long tile) {
+            const long long n0 = tile * TN;
+            const int nvalid = (int)min((long long)TN, p.N - n0);
+            for (int item = mt; item < TN * LPN; item += WS_MLP) {
+                const int i = item / LPN;
+                float* dstp = tb + i * SA + 4 * lig;
+                if (i < nvalid) cp_async16(dstp, p.x_in + (size_t)(p.row_offset + n0 + i) * DP + 4 * lig);
+                else st4(dstp, make_float4(0.f, 0.f, 0.f, 0.f));
+            }
+            for (int item = mt; item < TN * (CP / 4); item += WS_MLP) {
+                const int i = item / (CP / 4), c = item % (CP / 4);
+                float* dstp = tb + i * SA + 2 * DP + 4 * c;
+                if (i < nvalid) cp_async16(dstp, p.cst + (size_t)(n0 + i) * CP + 4 * c);
+                else st4(dstp, make_float4(0.f, 0.f, 0.f, 0.f));
+            }
+            cp_async_commit();
+        };
+        if (first + (long long)mgroup * stride < ntiles) issue_own(first + (long long)mgroup * stride);
+
         int it = mgroup;
         for (long long tile = first + (long long)mgroup * stride; tile < ntiles; tile += 2 * stride, it += 2) {
             const int b = mgroup;
             const long long n0 = tile * TN;
             const int nvalid = (int)min((long long)TN, p.N - n0);
-            float* tb = tile0 + (size_t)b * TN * SA;
-            named_bar_sync(GNN_BAR_FULL0 + b, WS_PAIR);
+            named_bar_sync(GNN_BAR_FULL0 + b, WS_PAIR);            // aggregates of this tile are in the buffer
+            cp_async_wait_group<0>();                              // my own / constant rows too ...
+            named_bar_sync(GNN_BAR_MLP0 + mgroup, WS_MLP);         // ... and those of the rest of the group
 
             // Dense layer: 4 nodes x 4 units per thread, k unrolled by 8
             float acc[4][4];
@@ -344,7 +346,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) state_iter_ws_kernel(const Iter
                     any_moving |= valid && (sqrtf(d2) > p.thr * sqrtf(o2));
                 }
             }
-            if (tile + 2 * stride < ntiles) {   // the gather warps wait for this buffer before prefetching tile it+2
+            if (tile + 2 * stride < ntiles) {   // this buffer's next tile: fetch its own rows, then hand the buffer back
+                named_bar_sync(GNN_BAR_MLP0 + mgroup, WS_MLP);   // the whole group has finished reading the tile
+                issue_own(tile + 2 * stride);
                 __threadfence_block();
                 named_bar_arrive(GNN_BAR_EMPTY0 + b, WS_PAIR);
             }
