@@ -479,14 +479,36 @@ class GraphTensor:
         return self._cached('filtered', lambda: torch.nonzero(self.set_mask[self.output_mask], as_tuple=False)[:, 0])
 
     def pool_nodes(self, out_nodes):
-        """ NodeGraph^T @ out_nodes (GNN.py:331-332) without the dense matrix: per-graph weighted segment sum """
+        """ NodeGraph^T @ out_nodes (GNN.py:331-332) without the dense matrix: per-graph weighted segment sum.
+        Merged batches keep the nodes of a graph contiguous, so the pooling is a CSR over graphs evaluated by the
+        library's SpMM kernel (stored order: deterministic); anything else falls back to index_add """
         import torch
         if self._ng_dense is not None: return self._ng_dense.t() @ out_nodes
         idx = self.mask_index()
+        if int(out_nodes.shape[0]) == int(self._ng_ids.shape[0]) and self._pool_csr() is not None:
+            from .state_loop import segment_pool
+            rowptr, col, ids64 = self._pool_csr()
+            return segment_pool(rowptr, col, self._ng_coeff, ids64, out_nodes)
         ids = self._ng_ids.to(torch.int64).index_select(0, idx)
         coeff = self._ng_coeff.index_select(0, idx)
         pooled = torch.zeros((self._ng_cols, out_nodes.shape[1]), dtype=out_nodes.dtype, device=out_nodes.device)
         return pooled.index_add(0, ids, coeff[:, None] * out_nodes)
+
+    def _pool_csr(self):
+        """ (rowptr over graphs, node index, int64 graph ids) when the graph ids are non-decreasing, else None """
+        import torch
+        cache = self.__dict__.setdefault('_pool_cache', dict())
+        key = id(self._ng_ids)
+        if key not in cache:
+            ids = self._ng_ids.to(torch.int64)
+            if ids.numel() > 1 and bool((ids[1:] < ids[:-1]).any()):
+                cache[key] = None
+            else:
+                counts = torch.bincount(ids, minlength=self._ng_cols)
+                rowptr = torch.zeros(self._ng_cols + 1, dtype=torch.int32, device=ids.device)
+                rowptr[1:] = torch.cumsum(counts, 0).to(torch.int32)
+                cache[key] = (rowptr, torch.arange(ids.numel(), dtype=torch.int32, device=ids.device), ids)
+        return cache[key]
 
     # -----------------------------------------------------------------------------------------------------------------
     def copy(self):

@@ -44,6 +44,25 @@ def sparse_dense(sp: SparseCSR, dense: torch.Tensor) -> torch.Tensor:
     return _SparseDense.apply(sp, dense.to(torch.float32))
 
 
+class _SegmentPool(torch.autograd.Function):
+    """ NodeGraph^T @ out_nodes for a block-diagonal NodeGraph kept as (graph id, coefficient) per node, graph ids
+    non-decreasing: a CSR over graphs evaluated by gnn_spmm (stored order, deterministic); GNN.py:331-332 """
+
+    @staticmethod
+    def forward(ctx, rowptr, col, coeff, ids, out_nodes):
+        ctx.save_for_backward(coeff, ids)
+        return N.spmm(rowptr, col, coeff, out_nodes)
+
+    @staticmethod
+    def backward(ctx, g_pooled):
+        coeff, ids = ctx.saved_tensors
+        return None, None, None, None, g_pooled.index_select(0, ids) * coeff[:, None]
+
+
+def segment_pool(rowptr, col, coeff, ids, out_nodes):
+    return _SegmentPool.apply(rowptr, col, coeff, ids, out_nodes.to(torch.float32))
+
+
 class _LoopConfig:
     __slots__ = ('adj', 'net', 'spec', 'D', 'NL_self', 'NL_agg', 'AL', 'max_iter', 'threshold', 'training', 'seed', 'save', 'partition')
 

@@ -285,3 +285,73 @@ def training_gradients(g, net_state, net_output, loss_fn, *, mean: bool = True, 
     gs = [torch.zeros_like(w) if gr is None else gr for w, gr in zip(ws, gs)]
     if mean: gs = [gr / k for gr in gs]
     return k, loss.detach(), gs, go, out.detach(), state.detach()
+
+
+# =====================================================================================================================
+# LGNN (GNN/LGNN.py:201-290)
+# =====================================================================================================================
+def lgnn_update_graph(g: OracleGraph, state, output, get_state: bool, get_output: bool, problem_based: str) -> OracleGraph:
+    """ GNN/LGNN.py:227-260: new graph whose node (arc) labels are the ORIGINAL labels ++ state ++ scatter_nd(where(mask),
+    output) -- zeros where the mask is off """
+    import copy
+    new = copy.copy(g)
+    extra_nodes, extra_arcs = [], []
+    if get_state: extra_nodes.append(state)
+    if get_output:
+        mask = g.set_mask & g.output_mask                                                  # :247
+        rows = g.arcs.shape[0] if problem_based == 'a' else g.nodes.shape[0]
+        out = torch.zeros((rows, output.shape[1]), dtype=output.dtype).index_put((torch.nonzero(mask)[:, 0],), output)  # :251
+        (extra_arcs if problem_based == 'a' else extra_nodes).append(out)                   # :253-256
+    if extra_nodes: new.nodes = torch.cat([g.nodes] + extra_nodes, dim=1)                   # :258
+    if extra_arcs: new.arcs = torch.cat([g.arcs] + extra_arcs, dim=1)                       # :259
+    return new
+
+
+def lgnn_loop(g: OracleGraph, nets: list, *, get_state: bool, get_output: bool, state_vect_dim: int, max_iteration: int,
+              threshold: float, training: bool, x0s=None, seeds=None, problem_based: str = 'n'):
+    """ GNN/LGNN.py:263-290: every layer runs the node-level Loop on the updated graph; for graph-based problems the
+    pooled output of the non-final layers only enters the output list (:276-278).
+    :param nets: list of (net_state, net_output) per layer; x0s / seeds: per-layer injected initial states / dropout seeds
+    :return: (list of k, state of the last layer, list of outputs) """
+    L = len(nets)
+    gtmp, K, outs = g, [], []
+    state = out = None
+    for idx, (net_s, net_o) in enumerate(nets):
+        last = idx == L - 1
+        node_level = 'n' if (problem_based == 'g' and not last) else problem_based
+        x0 = None if x0s is None else x0s[idx]
+        seed = 0 if seeds is None else seeds[idx]
+        k, state, out = loop(gtmp, net_s, net_o, state_vect_dim=state_vect_dim, max_iteration=max_iteration, threshold=threshold,
+                             training=training, x0=x0, seed=seed, problem_based=node_level)
+        K.append(k)
+        if problem_based == 'g' and not last:
+            outs.append(g.nodegraph.t() @ out)                                               # :278
+            gtmp = lgnn_update_graph(g, state, out, get_state, get_output, 'n')
+        else:
+            outs.append(out)
+            if not last: gtmp = lgnn_update_graph(g, state, out, get_state, get_output, problem_based)
+    return K, state, outs
+
+
+def lgnn_training_gradients(g, nets, loss_fn, *, training_mode: str, mean: bool = True, problem_based='n', **kw):
+    """ GNN/LGNN.py:201-224 + GNN_BaseClass.py:231-247: parallel -> sum_targets mean_i(loss(t, o_i) * w);
+    residual -> loss(t, mean_i o_i) * w; net_state gradients of layer i divided by its own k_i """
+    targs = filtered(g, g.targets, problem_based)
+    weights = filtered(g, g.sample_weights, problem_based)
+    K, state, outs = lgnn_loop(g, nets, training=True, problem_based=problem_based, **kw)
+    if training_mode == 'residual':
+        loss = (loss_fn(targs, torch.stack(outs, 0).mean(0)) * weights).sum()
+    else:
+        loss = torch.stack([loss_fn(targs, o) * weights for o in outs], 0).mean(0).sum()
+    gs, go = [], []
+    params = [p for net_s, net_o in nets for p in net_s.trainable() + net_o.trainable()]
+    grads = list(torch.autograd.grad(loss, params, allow_unused=True))
+    pos = 0
+    for (net_s, net_o), k in zip(nets, K):
+        ns, no = len(net_s.trainable()), len(net_o.trainable())
+        g_s = [torch.zeros_like(w) if gr is None else gr for w, gr in zip(net_s.trainable(), grads[pos:pos + ns])]
+        g_o = [torch.zeros_like(w) if gr is None else gr for w, gr in zip(net_o.trainable(), grads[pos + ns:pos + ns + no])]
+        gs.append([gr / k if mean else gr for gr in g_s])
+        go.append(g_o)
+        pos += ns + no
+    return K, loss.detach(), gs, go, [o.detach() for o in outs]
