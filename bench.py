@@ -68,6 +68,93 @@ def make_workload(name: str, N: int, E: int, seed: int = 0):
                 E=int(dst.shape[0]))
 
 
+def make_graph_batches(n_graphs: int, graphs_per_step: int, seed: int = 0):
+    """ MUTAG-shaped molecule-like graphs (N_g ~ clip(round(lognormal), 4, 417), mean ~30; symmetric sparse
+    arcs ~2.03 N_g: a chain plus a few chords), NL=14 one-hot, AL=3 one-hot, T=2, graph targets Bernoulli(.5); returned as
+    merged batches (disjoint unions) of `graphs_per_step` graphs, built directly as arrays """
+    from gnn_b200.graph_class import GraphObject
+    rng = np.random.default_rng(seed)
+    batches = []
+    for start in range(0, n_graphs, graphs_per_step):
+        G = min(graphs_per_step, n_graphs - start)
+        sizes = np.clip(np.rint(rng.lognormal(np.log(26.0), 0.5, G)), 4, 417).astype(np.int64)
+        offs = np.concatenate([[0], np.cumsum(sizes)])
+        N = int(offs[-1])
+        gid = np.repeat(np.arange(G), sizes)
+        local = np.arange(N) - offs[gid]
+        chain = np.nonzero(local < sizes[gid] - 1)[0]                     # i -> i+1 inside a graph
+        n_chords = np.maximum(1, np.rint(0.015 * sizes)).astype(np.int64)
+        cg = np.repeat(np.arange(G), n_chords)
+        ca = offs[cg] + (rng.random(len(cg)) * sizes[cg]).astype(np.int64)
+        cb = offs[cg] + (rng.random(len(cg)) * sizes[cg]).astype(np.int64)
+        keep = ca != cb
+        a = np.concatenate([chain, ca[keep]]); b = np.concatenate([chain + 1, cb[keep]])
+        lab = rng.integers(0, 3, len(a))
+        src, dst = np.concatenate([a, b]), np.concatenate([b, a])
+        order = np.lexsort((dst, src))
+        src, dst, lab2 = src[order], dst[order], np.concatenate([lab, lab])[order]
+        arcs = np.zeros((len(src), 5), dtype=np.float32)
+        arcs[:, 0], arcs[:, 1] = src, dst
+        arcs[np.arange(len(src)), 2 + lab2] = 1
+        nodes = np.eye(14, dtype=np.float32)[rng.integers(0, 14, N)]
+        targets = np.eye(2, dtype=np.float32)[rng.integers(0, 2, G)]
+        nodegraph = ('segments', gid, (1.0 / sizes[gid]).astype(np.float32), G)
+        batches.append(GraphObject(arcs=arcs, nodes=nodes, targets=targets, problem_based='g', NodeGraph=nodegraph,
+                                   aggregation_mode='average', _endpoints=(src, dst)))
+    return batches
+
+
+def bench_graph_batches(args, device, rank, world):
+    """ C5 leg: graph batches sharded by whole graph over the ranks (weak scaling: 25 000 graphs per rank), one
+    training_step (forward + BPTT + flat gradient all-reduce + Adam) per merged batch """
+    import torch
+    import torch.distributed as dist
+    from gnn_b200 import _native
+    from gnn_b200.graph_class import GraphTensor
+    from gnn_b200.GNN import GNNgraphBased
+    from gnn_b200.keras_compat import Dense, Sequential, Adam, categorical_crossentropy
+    per_rank, per_step = args.graphs_per_rank, args.graphs_per_step
+    batches = make_graph_batches(per_rank, per_step, seed=1000 + rank)
+    gts = [GraphTensor.fromGraphObject(b, device=device) for b in batches]
+    arcs = sum(int(b.arcs.shape[0]) for b in batches)
+    rng = np.random.default_rng(0)     # identical (replicated) initial weights on every rank
+    net_s = Sequential([Dense(14, activation='selu')], input_dim=31, device=device)
+    net_o = Sequential([Dense(2, activation='softmax')], input_dim=14, device=device)
+    net_s.set_weights([(rng.standard_normal((31, 14)) / np.sqrt(31)).astype(np.float32), np.zeros(14, np.float32)])
+    net_o.set_weights([(rng.standard_normal((14, 2)) / np.sqrt(8)).astype(np.float32), np.zeros(2, np.float32)])
+    gnn = GNNgraphBased(net_s, net_o, Adam(1e-3), categorical_crossentropy, {'from_logits': False}, state_vect_dim=0, max_iteration=5,
+                        threshold=0.01, addressed_problem='c', path_writer=f'/tmp/gnn_b200_bench_c5_{rank}/')
+    gnn.distributed = world > 1
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ks = []
+
+    def epoch():
+        for gt in gts:
+            iters, _ = gnn.training_step(gt)
+            ks.append(iters[0])
+
+    for _ in range(max(1, args.warmup // 3)): epoch()
+    torch.cuda.synchronize()
+    if world > 1: dist.barrier()
+    _native.launch_count(reset=True)
+    start.record()
+    for _ in range(args.steps): epoch()
+    stop.record()
+    torch.cuda.synchronize()
+    if world > 1: dist.barrier()
+    ms = torch.tensor([start.elapsed_time(stop) / args.steps], device=device)
+    upd = torch.tensor([float(sum(float(k) for k in ks[-len(gts):]) / len(gts)) * arcs], device=device)   # arcs x iterations of one epoch
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(upd, op=dist.ReduceOp.SUM)
+    return {'value': float(upd.item()) / (float(ms.item()) * 1e-3), 'ms_per_step': float(ms.item()), 'epoch_time_s': float(ms.item()) * 1e-3,
+            'gpu_launches': int(_native.launch_count() // args.steps),
+            'config': {'workload': f'c5: {per_rank} MUTAG-shaped graphs per rank ({per_rank * world} in total), merged batches of {per_step}, '
+                                   f'graph classification, NL 14, AL 3, state = labels (D 14), max_iteration 5, threshold 0.01, one '
+                                   f'training_step (forward + BPTT + gradient all-reduce + Adam) per batch; step = one epoch of the shard',
+                       'arcs_per_rank': arcs}}
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # clocks sampling during the timed region
 # ---------------------------------------------------------------------------------------------------------------------
@@ -143,7 +230,9 @@ def main():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--workload', default='c4u', choices=['c4u', 'c4l'])
+    ap.add_argument('--workload', default='c4u', choices=['c4u', 'c4l', 'c5'])
+    ap.add_argument('--graphs-per-rank', type=int, default=25_000)
+    ap.add_argument('--graphs-per-step', type=int, default=5_000)
     ap.add_argument('--nodes', type=int, default=1_000_000)
     ap.add_argument('--arcs', type=int, default=10_000_000)
     ap.add_argument('--max-iter', type=int, default=50)
@@ -195,6 +284,16 @@ def main():
         dist.init_process_group('nccl', device_id=device)
 
     from gnn_b200 import dist_graph
+    if args.workload == 'c5':   # graph-batch sharding (weak scaling); not the headline workload
+        with ClockSampler(local_rank) as clocks:
+            res = bench_graph_batches(args, device, rank, world)
+        if rank == 0:
+            res.update({'metric': 'arc-updates/sec (arcs x iterations), forward+backward+optimizer, sharded graph batches', 'unit': 'arc-updates/s',
+                        'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'higher_is_better': True, 'scaling': 'weak',
+                        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'clocks': clocks.summary()})
+            print(json.dumps(res))
+        if world > 1: dist.destroy_process_group()
+        return
     wl = make_workload(args.workload, args.nodes, args.arcs)
     N, E = wl['N'], wl['E']
 
@@ -210,10 +309,15 @@ def main():
     g_host = GraphObject(arcs=wl['arcs'], nodes=wl['nodes'], targets=wl['targets'], problem_based='n', aggregation_mode='average',
                          _endpoints=(wl['src'], wl['dst']))
     if world > 1:
-        result = dist_graph.bench_partitioned(g_host, wl, build_gnn, args, device, rank, world)
+        with ClockSampler(local_rank) as clocks:
+            result = dist_graph.bench_partitioned(g_host, wl, build_gnn, args, device, rank, world)
         if rank == 0:
-            result.update({'metric': metric, 'unit': 'arc-updates/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
-                           'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': config})
+            config['partition'] = result.pop('partition')
+            result.update({'metric': metric, 'unit': 'arc-updates/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(3, args.warmup),
+                           'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+                           'config': config, 'cpu_baseline': None, 'clocks': clocks.summary(),
+                           'roofline': {'bound': 'nvlink+hbm', 'note': 'per-iteration exchange of the state rows other ranks gather from: see '
+                                        'config.partition.halo_bytes_received_per_iteration_per_rank; single-GPU kernel roofline in the N=1 line'}})
             print(json.dumps(result))
         dist.destroy_process_group()
         return

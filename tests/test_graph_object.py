@@ -193,3 +193,14 @@ def test_random_graph_reproduces_reference_with_seed(golden_dir, pb):
     np.random.seed(7)
     glist = [utils.randomGraph(int(n), 3, 1, 2, 0.7, aggregation_mode='average', problem_based=pb) for n in (15, 22, 17, 30, 9)]
     _check_graph(glist[1], ref)
+
+
+@pytest.mark.skipif(not os.path.exists('/root/reference/MUTAG_raw/Mutagenicity_edges.txt'), reason='MUTAG raw files are not shipped')
+def test_mutag_loader_counts():
+    """ restated loader (NumPy 2) reproduces the dataset statistics measured with the reference recipe """
+    from gnn_b200.load_MUTAG import load_MUTAG
+    graphs = load_MUTAG('/root/reference/MUTAG_raw/')
+    assert len(graphs) == 4337
+    assert sum(g.nodes.shape[0] for g in graphs) == 131488 and sum(g.arcs.shape[0] for g in graphs) == 266894
+    assert graphs[0].DIM_NODE_LABEL == 14 and graphs[0].DIM_ARC_LABEL == 3 and graphs[0].DIM_TARGET == 2
+    assert graphs[0].NodeGraph.shape == (graphs[0].nodes.shape[0], 1)
