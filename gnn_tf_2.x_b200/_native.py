@@ -51,7 +51,8 @@ class gnn_loop_args(C.Structure):
                 ('max_iter', C.c_int32), ('threshold', C.c_float), ('training', C.c_int32),
                 ('save_for_backward', C.c_int32), ('seed', C.c_uint32),
                 ('x_out', C.c_void_p), ('k_out', C.c_void_p),
-                ('n_global', C.c_int64), ('row_offset', C.c_int64), ('exchange', C.c_void_p), ('exchange_user', C.c_void_p)]
+                ('n_global', C.c_int64), ('row_offset', C.c_int64), ('exchange', C.c_void_p), ('exchange_user', C.c_void_p),
+                ('n_peers', C.c_int32), ('rank', C.c_int32), ('peer_state', C.c_void_p * 8), ('peer_mask', C.c_void_p)]
 
 
 # callback type of gnn_loop_args.exchange: (user, t, x_next_offset, go_next_offset)
@@ -60,7 +61,7 @@ EXCHANGE_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int32, C.c_int64, C.c_int64)
 
 # every symbol include/gnn_b200.h declares (tests check that the library exports all of them)
 EXPORTED_SYMBOLS = ['gnn_last_error', 'gnn_abi_version', 'gnn_device_info', 'gnn_csr_build', 'gnn_spmm',
-                    'gnn_state_loop_workspace_bytes', 'gnn_state_loop_forward', 'gnn_state_loop_backward',
+                    'gnn_state_loop_workspace_bytes', 'gnn_state_loop_layout', 'gnn_state_loop_forward', 'gnn_state_loop_backward',
                     'gnn_launch_count', 'gnn_profile_iterations', 'gnn_profile_last_iterations']
 
 
@@ -88,6 +89,9 @@ def lib() -> C.CDLL:
                                C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]
         l.gnn_state_loop_workspace_bytes.argtypes = [C.POINTER(gnn_graph), C.POINTER(gnn_mlp), C.POINTER(gnn_loop_args),
                                                      C.POINTER(C.c_size_t)]
+        l.gnn_state_loop_layout.argtypes = [C.POINTER(gnn_graph), C.POINTER(gnn_mlp), C.POINTER(gnn_loop_args),
+                                            C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+        l.gnn_state_loop_layout.restype = C.c_int
         l.gnn_state_loop_forward.argtypes = [C.POINTER(gnn_graph), C.POINTER(gnn_mlp), C.POINTER(gnn_loop_args),
                                              C.c_void_p, C.c_size_t, C.c_void_p]
         l.gnn_state_loop_backward.argtypes = [C.POINTER(gnn_graph), C.POINTER(gnn_mlp), C.POINTER(gnn_loop_args), C.c_void_p,

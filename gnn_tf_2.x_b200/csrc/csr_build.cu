@@ -7,12 +7,14 @@
 // the rest (key packing, row pointers with empty rows, gathers, uniformity test) are our kernels.
 #include <cub/device/device_radix_sort.cuh>
 
+#include <atomic>
+
 #include "common.cuh"
 
 namespace gnn {
 
 static thread_local std::string g_last_error;
-static thread_local int64_t g_launches = 0;
+static std::atomic<int64_t> g_launches{0};   // process-wide: the backward pass runs on autograd's own thread
 void set_error(const std::string& msg) { g_last_error = msg; }
 void count_launch(int n) { g_launches += n; }
 
@@ -97,8 +99,8 @@ using namespace gnn;
 extern "C" const char* gnn_last_error(void) { return g_last_error.c_str(); }
 extern "C" int gnn_abi_version(void) { return GNN_B200_ABI_VERSION; }
 extern "C" int64_t gnn_launch_count(int32_t reset) {
-    int64_t v = g_launches;
-    if (reset) g_launches = 0;
+    int64_t v = g_launches.load();
+    if (reset) g_launches.store(0);
     return v;
 }
 

@@ -26,6 +26,9 @@ struct IterParams {
     const float* val;        // NULL => row scale in cst[:, C]
     long long N;
     long long row_offset;    // global id of local row 0 (node-range partition; 0 on a single GPU)
+    int n_peers, rank;       // fused NVLink exchange: new rows are also stored into the peers' state buffers
+    float* peer_out[GNN_MAX_PEERS];
+    const uint32_t* peer_mask;
     // state
     const float* x_in;       // [N, DP]
     float* x_out;            // [N, DP]  (pre-BN output h_t when bn_train)
@@ -139,6 +142,15 @@ __device__ __forceinline__ void cp_async16_hint(float* smem_dst, const float* gm
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+// store one 16-byte piece of a new state row into the state buffers of the peers that gather from this row
+__device__ __forceinline__ void store_to_peers(const IterParams& p, long long local_row, int col4, float4 v) {
+    const uint32_t need = p.peer_mask ? __ldg(p.peer_mask + local_row) : 0xffffffffu;
+    const size_t off = (size_t)(p.row_offset + local_row) * (size_t)p.net.DP + col4;
+#pragma unroll
+    for (int r = 0; r < GNN_MAX_PEERS; ++r)
+        if (r < p.n_peers && r != p.rank && ((need >> r) & 1u)) *reinterpret_cast<float4*>(p.peer_out[r] + off) = v;
+}
 
 __device__ __forceinline__ float drop1(float v, bool active, uint32_t key, uint64_t idx, float rate, float scale) {
     if (!active) return v;
@@ -383,6 +395,7 @@ __global__ void __launch_bounds__(NT, GNN_FWD_MIN_CTAS) state_iter_kernel(const 
             float d2 = 0.f, o2 = 0.f;
             if (valid) {
                 st4_hint(p.x_out + (size_t)(p.row_offset + n) * DP + 4 * lig, xn, stream_pol);
+                if (p.n_peers > 1) store_to_peers(p, n, 4 * lig, xn);
                 if (p.bn_train) {
                     bn_s1[0] += xn.x; bn_s1[1] += xn.y; bn_s1[2] += xn.z; bn_s1[3] += xn.w;
                     bn_s2[0] += (double)xn.x * xn.x; bn_s2[1] += (double)xn.y * xn.y;
@@ -438,6 +451,7 @@ __global__ void __launch_bounds__(NT, GNN_FWD_MIN_CTAS) state_iter_kernel(const 
             for (int c = 0; c < 4; ++c) { dst[4 * tid + c] = s1[c]; dst[DP + 4 * tid + c] = s2[c]; }
         }
     } else {
+        if (p.n_peers > 1) __threadfence_system();   // peer stores performed before the kernel is reported complete
         if (tid == 0) {
             if (p.go_next && s_flag) atomicOr(p.go_next, 1);
             if (blockIdx.x == 0) *p.k_ptr = p.t + 1;

@@ -326,6 +326,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) state_iter_ws_kernel(const Iter
                 float d2 = 0.f, o2 = 0.f;
                 if (valid) {
                     st4_hint(p.x_out + (size_t)(p.row_offset + n) * DP + 4 * lig, xn, stream_pol);
+                    if (p.n_peers > 1) store_to_peers(p, n, 4 * lig, xn);
                     if (p.bn_train) {
                         bn_s1[0] += xn.x; bn_s1[1] += xn.y; bn_s1[2] += xn.z; bn_s1[3] += xn.w;
                         bn_s2[0] += (double)xn.x * xn.x; bn_s2[1] += (double)xn.y * xn.y;
@@ -380,6 +381,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) state_iter_ws_kernel(const Iter
             }
         } else {
             if (p.go_next && __any_sync(0xffffffffu, any_moving) && (tid & 31) == 0) s_flag = 1;
+            if (p.n_peers > 1) __threadfence_system();   // peer stores performed before the kernel is reported complete
             named_bar_sync(GNN_BAR_MLP_ALL, WS_MLP_ALL);
             if (tid == 0) {
                 if (p.go_next && s_flag) atomicOr(p.go_next, 1);

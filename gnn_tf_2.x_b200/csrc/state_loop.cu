@@ -157,8 +157,10 @@ int check_args(const gnn_graph* g, const gnn_mlp* net, const gnn_loop_args* a) {
     if (a->n_global > 0) {
         if (a->row_offset < 0 || a->row_offset + g->n_nodes > a->n_global) GNN_FAIL(GNN_ERR_INVALID, "partition rows outside the graph");
         if (a->training || a->save_for_backward) GNN_FAIL(GNN_ERR_UNSUPPORTED, "partitioned calls are forward-only");
-    } else if (a->row_offset != 0 || a->exchange) {
-        GNN_FAIL(GNN_ERR_INVALID, "row_offset / exchange need n_global");
+        if (a->n_peers < 0 || a->n_peers > GNN_MAX_PEERS) GNN_FAIL(GNN_ERR_INVALID, "n_peers outside 0..%d", GNN_MAX_PEERS);
+        if (a->n_peers > 1 && (a->rank < 0 || a->rank >= a->n_peers)) GNN_FAIL(GNN_ERR_INVALID, "rank outside 0..n_peers-1");
+    } else if (a->row_offset != 0 || a->exchange || a->n_peers > 1) {
+        GNN_FAIL(GNN_ERR_INVALID, "row_offset / exchange / peers need n_global");
     }
     for (int l = 0; l <= net->n_layers && l <= GNN_MAX_LAYERS; ++l)
         if (net->drop_rate[l] > 0.f && a->training == 0) { /* inactive in inference */ }
@@ -309,6 +311,7 @@ extern "C" int gnn_state_loop_forward(const gnn_graph* g, const gnn_mlp* net, co
     p.rowptr = g->rowptr; p.col = g->col; p.val = plan.has_val ? g->val : nullptr; p.N = N; p.row_offset = a->row_offset;
     p.cst = w.cst; p.wpack = w.wpack; p.k_ptr = kptr; p.thr = a->threshold; p.bn_partial = w.bn_partial;
     p.bn_train = bn_train; p.seed = a->seed; p.training = a->training; p.scol_cap = plan.scol_cap; p.net = lay;
+    p.n_peers = a->n_global > 0 ? a->n_peers : 0; p.rank = a->rank; p.peer_mask = a->peer_mask;
     BnApplyKernel bn_apply = kernel_set(lay.DP)->bn_apply;
 
     if (g_profile.enabled) {
@@ -324,6 +327,7 @@ extern "C" int gnn_state_loop_forward(const gnn_graph* g, const gnn_mlp* net, co
         p.go_cur = go + t;
         p.go_next = (t + 1 < a->max_iter) ? go + t + 1 : nullptr;
         p.t = t;
+        for (int r = 0; r < p.n_peers; ++r) p.peer_out[r] = a->peer_state[r] ? a->peer_state[r] + (size_t)((t + 1) & 1) * w.slab : nullptr;
         if (N > 0) {
             void* args[] = {(void*)&p};
             GNN_CUDA(cudaLaunchKernel((const void*)plan.kernel, dim3(plan.grid), dim3(plan.ts.nt), args, plan.smem, stream));
@@ -351,6 +355,18 @@ extern "C" int gnn_state_loop_forward(const gnn_graph* g, const gnn_mlp* net, co
     finalize_kernel<<<(unsigned)ceil_div(std::max<long long>(NGLOB * lay.D, 1), 256), 256, 0, stream>>>(
         kptr, w.X, (long long)w.slab, save ? 0 : 2, NGLOB, lay.D, lay.DP, a->x_out, a->k_out);
     GNN_LAUNCH_CHECK();
+    return GNN_OK;
+}
+
+extern "C" int gnn_state_loop_layout(const gnn_graph* g, const gnn_mlp* net, const gnn_loop_args* a, size_t* state_offset, size_t* state_bytes) {
+    GNN_TRY(check_args(g, net, a));
+    NetLayout lay;
+    GNN_TRY(make_layout(net, 1, a->D, a->NL_self, a->NL_agg, a->AL, 128, 128, &lay));
+    Workspace w;
+    char probe[1];   // carve only computes offsets relative to the base
+    GNN_TRY(carve(g, a, lay, probe, &w));
+    if (state_offset) *state_offset = (size_t)((char*)w.X - probe);
+    if (state_bytes) *state_bytes = w.slab * 4;
     return GNN_OK;
 }
 

@@ -95,11 +95,21 @@ class HaloPlan:
         return int(self.recv_rows.numel()) * row_bytes
 
 
+_SYMMETRIC_WORKSPACES: dict = dict()
+
+
 class GraphPartition:
     """ rows [lo, hi) of one GraphObject on this rank: local CSRs with global column ids + replicated labels.
-    Passed as ``partition=`` to ``state_loop`` (attributes n_global, row_offset, exchange). """
+    Passed as ``partition=`` to ``state_loop`` (attributes n_global, row_offset, exchange).
 
-    def __init__(self, g, rank: int, world: int, device=None, group=None):
+    Exchange of the boundary state rows after every iteration, two implementations:
+      * fused (default when peer memory is available): the loop's workspace lives in symmetric memory
+        (torch.distributed._symmetric_memory), the iteration kernel stores each new row straight into the state buffers of
+        the peers that gather from it (NVLink P2P stores overlapped with the MLP of the next tiles) and the callback only
+        max-reduces the convergence flag -- which is also the barrier that orders the iterations across ranks;
+      * NCCL: all-gather / all-to-all of the rows after the kernel (``fused=False`` or when symmetric memory is refused). """
+
+    def __init__(self, g, rank: int, world: int, device=None, group=None, fused: bool = True):
         from . import _native
         from .graph_class import GraphObject
         assert isinstance(g, GraphObject)
@@ -129,15 +139,69 @@ class GraphPartition:
         self.nodes = f32(g.nodes)                                 # replicated (label widths are small)
         self.n_arcs_local = n_mine
         self.halo = HaloPlan(self.Adjacency.col, self.bounds, rank, world, group) if world > 1 else None
+        self.fused = bool(fused and world > 1 and world <= 8 and self.device.type == 'cuda')
+        self._ws = self._handle = self._peer_mask = self._state_offsets = None
+        self._order = torch.zeros(1, dtype=torch.int32, device=self.device) if world > 1 else None
+        if self.fused: self._build_peer_mask()
+
+    # ---- fused exchange over peer memory --------------------------------------------------------------------------
+    def _build_peer_mask(self):
+        """ bit r of peer_mask[local row] = rank r gathers from that row; None when every peer needs (almost) every row """
+        if self.halo.use_allgather:
+            self._peer_mask = None
+            return
+        mask = torch.zeros(self.n_local, dtype=torch.int64, device=self.device)
+        pos = 0
+        for r, count in enumerate(self.halo.send_counts):
+            if count: mask.index_add_(0, self.halo.send_rows[pos:pos + count] - self.row_offset, torch.full((count,), 1 << r, dtype=torch.int64, device=self.device))
+            pos += count
+        self._peer_mask = mask.to(torch.int32)     # rows are unique per peer, so the sum is the OR of the bits
+
+    def alloc_workspace(self, nbytes: int) -> torch.Tensor:
+        if not self.fused: return torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        # one symmetric workspace per (device, group), shared by every partition object of the process: the collective
+        # allocation + rendezvous costs milliseconds and the loop calls are ordered on the stream anyway
+        key = (str(self.device), id(self.group))
+        cached = _SYMMETRIC_WORKSPACES.get(key)
+        need = torch.tensor([nbytes], dtype=torch.int64, device=self.device)
+        dist.all_reduce(need, op=dist.ReduceOp.MAX, group=self.group)              # same decision on every rank
+        if cached is None or cached[0].numel() < int(need.item()):
+            try:
+                import torch.distributed._symmetric_memory as symm
+                ws = symm.empty(int(need.item()), dtype=torch.uint8, device=self.device)
+                handle = symm.rendezvous(ws, group=self.group if self.group is not None else dist.group.WORLD)
+                cached = _SYMMETRIC_WORKSPACES[key] = (ws, handle)
+            except Exception as exc:                                                 # no peer mapping on this system: NCCL exchange
+                self.fused, self._fused_error = False, repr(exc)
+                return torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        if self._ws is not cached[0]: self._state_offsets = None
+        self._ws, self._handle = cached
+        return self._ws
+
+    def peer_setup(self, args, workspace, state_offset: int) -> None:
+        if self.world == 1: return
+        # order this call after everything the peers did with the shared buffers in the previous call
+        dist.all_reduce(self._order, op=dist.ReduceOp.MAX, group=self.group)
+        if not self.fused: return
+        if self._state_offsets is None:
+            mine = torch.tensor([state_offset], dtype=torch.int64, device=self.device)
+            every = [torch.zeros_like(mine) for _ in range(self.world)]
+            dist.all_gather(every, mine, group=self.group)
+            self._state_offsets = [int(t.item()) for t in every]
+        args.n_peers, args.rank = self.world, self.rank
+        for r in range(self.world): args.peer_state[r] = int(self._handle.buffer_ptrs[r]) + self._state_offsets[r]
+        args.peer_mask = None if self._peer_mask is None else self._peer_mask.data_ptr()
 
     def exchange(self, t: int, x_full: torch.Tensor, go_flag: Optional[torch.Tensor]) -> None:
         if self.world == 1: return
-        self.halo.exchange(x_full)
-        if go_flag is not None: dist.all_reduce(go_flag, op=dist.ReduceOp.MAX, group=self.group)
+        if not self.fused: self.halo.exchange(x_full)      # fused: the kernel has already stored the rows into the peers
+        # max-reduce of the flag = every rank runs the same iterations; it is also the cross-GPU barrier between iterations
+        dist.all_reduce(go_flag if go_flag is not None else self._order, op=dist.ReduceOp.MAX, group=self.group)
 
 
 def partitioned_loop(gnn, part: GraphPartition, x0: Optional[torch.Tensor] = None, seed: int = 0):
-    """ GNNnodeBased.Loop (inference) on one node range; returns (k, full state [n_global, D], outputs of the LOCAL rows).
+    """ GNNnodeBased.Loop (inference) on one node range; returns (k, state [n_global, D], outputs of the LOCAL rows).
+    In the returned state the rows of this rank and the rows it gathers from are valid (all rows when every row travels).
     Same arithmetic as the single-GPU call: the result does not depend on the number of ranks. """
     from .state_loop import state_loop, sparse_dense
     gnn.to(part.device)
@@ -213,5 +277,7 @@ def bench_partitioned(g_host, wl, build_gnn, args, device, rank, world):
     return {'value': E * k_fwd / (ms_fwd * 1e-3), 'ms_per_step': ms_fwd, 'iterations': k_fwd, 'gpu_launches': int(launches),
             'e2e': {'value': E * k_fwd / (ms_e2e * 1e-3), 'unit': 'arc-updates/s', 'ms_per_step': ms_e2e,
                     'h2d_bytes_per_step': int(local_bytes), 'd2h_bytes_per_step': int(held[-1].numel() * 4)},
-            'partition': {'ranks': world, 'rows_per_rank': part.n_local, 'exchange': 'all_gather' if part.halo.use_allgather else 'all_to_all',
+            'partition': {'ranks': world, 'rows_per_rank': part.n_local,
+                          'exchange': ('fused NVLink peer stores in the iteration kernel' if part.fused else 'NCCL ') +
+                                      (' (every row to every peer)' if part.halo.use_allgather else ' (boundary rows only)'),
                           'halo_bytes_received_per_iteration_per_rank': int(halo)}}

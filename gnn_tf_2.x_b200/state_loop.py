@@ -98,8 +98,16 @@ class _StateLoop(torch.autograd.Function):
         nbytes = C.c_size_t(0)
         N.check(lib.gnn_state_loop_workspace_bytes(C.byref(graph), C.byref(mlp), C.byref(args), C.byref(nbytes)),
                 'gnn_state_loop_workspace_bytes')
-        workspace = torch.empty(nbytes.value, dtype=torch.uint8, device=device)
+        if part is not None and hasattr(part, 'alloc_workspace'):
+            workspace = part.alloc_workspace(nbytes.value)        # peer-mapped (symmetric) memory when the exchange is fused
+        else:
+            workspace = torch.empty(nbytes.value, dtype=torch.uint8, device=device)
         callback, failure = None, []
+        if part is not None and hasattr(part, 'peer_setup'):
+            off, sbytes = C.c_size_t(0), C.c_size_t(0)
+            N.check(lib.gnn_state_loop_layout(C.byref(graph), C.byref(mlp), C.byref(args), C.byref(off), C.byref(sbytes)),
+                    'gnn_state_loop_layout')
+            part.peer_setup(args, workspace, int(off.value))      # fills n_peers / rank / peer_state / peer_mask, orders the call
         if part is not None:
             DP = 4
             while DP < cfg.D: DP *= 2

@@ -25,8 +25,9 @@
 extern "C" {
 #endif
 
-#define GNN_B200_ABI_VERSION 2
+#define GNN_B200_ABI_VERSION 3
 #define GNN_MAX_LAYERS 4 /* Dense layers per MLP */
+#define GNN_MAX_PEERS 8  /* GPUs of one NVSwitch domain */
 
 enum gnn_error {
     GNN_OK = 0,
@@ -157,9 +158,23 @@ typedef struct gnn_loop_args {
     int64_t row_offset;
     void (*exchange)(void* user, int32_t t, int64_t x_next_offset, int64_t go_next_offset);
     void* exchange_user;
+    /* Fused exchange over NVLink peer memory (optional, partitioned calls only).  When n_peers > 1 the workspace of
+     * every rank lives in peer-mapped (symmetric) memory and peer_state[r] is the address, valid on THIS device, of the
+     * state-buffer area of rank r's workspace (workspace_r + state offset from gnn_state_loop_layout).  The iteration
+     * kernel then stores every new state row it produces directly into the buffers of the peers that gather from it
+     * (peer_mask[local row] bit r; NULL = every peer needs every row), overlapping the transfer with the MLP of the
+     * following tiles; the exchange callback only has to max-reduce the flag (which also orders the iterations). */
+    int32_t n_peers;
+    int32_t rank;
+    float* peer_state[GNN_MAX_PEERS];
+    const uint32_t* peer_mask;
 } gnn_loop_args;
 
 int gnn_state_loop_workspace_bytes(const gnn_graph* g, const gnn_mlp* net, const gnn_loop_args* a, size_t* bytes);
+
+/* where the state buffers sit inside the workspace: byte offset of the first one and bytes per buffer ([rows, DP] fp32,
+ * rows = n_global when partitioned); forward-only calls ping-pong between buffer 0 and 1 */
+int gnn_state_loop_layout(const gnn_graph* g, const gnn_mlp* net, const gnn_loop_args* a, size_t* state_offset, size_t* state_bytes);
 
 int gnn_state_loop_forward(const gnn_graph* g, const gnn_mlp* net, const gnn_loop_args* a,
                            void* workspace, size_t workspace_bytes, void* stream);
