@@ -277,6 +277,7 @@ def main():
     from gnn_b200.GNN import GNNnodeBased
     from gnn_b200.keras_compat import Dense, BatchNormalization, Sequential, Adam, categorical_crossentropy
     if not torch.cuda.is_available(): raise SystemExit('bench.py needs a CUDA device')
+    torch.set_num_threads(1)     # the host side only enqueues: intra-op CPU threads just add wake-up latency (the CPU port sets its own)
     torch.cuda.set_device(local_rank)
     device = torch.device('cuda', local_rank)
     if world > 1:

@@ -90,7 +90,8 @@ static __global__ void init_state_kernel(const float* __restrict__ x0, long long
         }
         moving = sqrtf(d2) > thr * sqrtf((float)D);
     }
-    if (max_iter > 0 && __any_sync(0xffffffffu, moving) && (threadIdx.x & 31) == 0) atomicOr(go0, 1);
+    const int block_moving = __syncthreads_or(moving ? 1 : 0);
+    if (max_iter > 0 && block_moving && threadIdx.x == 0 && *reinterpret_cast<volatile int*>(go0) == 0) atomicOr(go0, 1);
 }
 
 // mean / biased variance of h over the nodes from the per-CTA partial sums (fp64), the normalisation
@@ -147,7 +148,9 @@ static __global__ void bn_apply_kernel(const int* __restrict__ go_cur, int* __re
         o2 += __shfl_xor_sync(0xffffffffu, o2, off);
     }
     const bool moving = valid && (sqrtf(d2) > thr * sqrtf(o2));
-    if (go_next && __any_sync(0xffffffffu, moving) && (threadIdx.x & 31) == 0) atomicOr(go_next, 1);
+    // one atomic per CTA at most, and none once the flag is up (every CTA hitting one address serialises in L2)
+    const int block_moving = __syncthreads_or(moving ? 1 : 0);
+    if (go_next && block_moving && threadIdx.x == 0 && *reinterpret_cast<volatile int*>(go_next) == 0) atomicOr(go_next, 1);
     if (item == 0) *k_ptr = t + 1;
 }
 

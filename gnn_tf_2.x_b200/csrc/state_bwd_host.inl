@@ -91,7 +91,8 @@ extern "C" int gnn_state_loop_backward(const gnn_graph* g, const gnn_mlp* net, c
     p.row_scale_mode = has_val ? 0 : 1; p.bn_eps = net->bn_eps; p.net = lay; p.has_dB = need_dB ? 1 : 0;
     ScatterKernel scatter = ks->scatter[has_val ? 1 : 0];
     BnBwdReduceKernel bn_reduce = ks->bn_bwd_reduce;
-    const int red_grid = (int)std::min<long long>(w.max_ctas, std::max<long long>(1, ceil_div(N * (lay.DP / 4), 256)));
+    // grid-stride reduction: a few CTAs per SM; the finalize kernel walks the partials serially, so keep them few
+    const int red_grid = (int)std::min<long long>(2LL * di.sms, std::max<long long>(1, ceil_div(N * (lay.DP / 4), 256)));
     const long long items = N * (lay.DP / 4);
 
     for (int t = a->max_iter - 1; t >= 0; --t) {
