@@ -298,53 +298,47 @@ __global__ void __launch_bounds__(WS_THREADS, 1) state_iter_ws_kernel(const Iter
                     }
                 }
             }
-            named_bar_sync(GNN_BAR_MLP0 + mgroup, WS_MLP);   // every thread of the group has read the aggregate columns: overwrite in place
+            // epilogue straight from the accumulators: bias + activation + affine, 128-bit store of the new state (8 lanes
+            // = one 128-byte row), convergence test reduced over the CG lanes that share a node
             if (has_item) {
+                const float4 b4 = ld4(bias + 4 * cg), a4 = ld4(aff_a + 4 * cg), c4 = ld4(aff_c + 4 * cg);
+                const float bb[4] = {b4.x, b4.y, b4.z, b4.w}, aa[4] = {a4.x, a4.y, a4.z, a4.w}, cc[4] = {c4.x, c4.y, c4.z, c4.w};
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    st4(tb + (ng + NG * i) * SA + DP + 4 * cg, make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));
-            }
-            named_bar_sync(GNN_BAR_MLP0 + mgroup, WS_MLP);
-
-            // bias + activation + affine, store, convergence test: lane group (LPN lanes) per node row
+                for (int i = 0; i < 4; ++i) {
+                    const int row = ng + NG * i;
+                    const long long n = n0 + row;
+                    const bool valid = row < nvalid;
+                    float v[4];
 #pragma unroll
-            for (int item = mt; item < TN * LPN; item += WS_MLP) {
-                const int i = item / LPN;
-                const long long n = n0 + i;
-                const bool valid = i < nvalid;
-                const float4 z = ld4(tb + i * SA + DP + 4 * lig);
-                const float4 b4 = ld4(bias + 4 * lig);
-                float v[4] = {z.x + b4.x, z.y + b4.y, z.z + b4.z, z.w + b4.w};
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const int j = 4 * lig + c;
-                    float y = act_apply(act, v[c]);
-                    if (affine) y = fmaf(aff_a[j], y, aff_c[j]);
-                    v[c] = (j < D) ? y : 0.f;
-                }
-                const float4 xn = make_float4(v[0], v[1], v[2], v[3]);
-                float d2 = 0.f, o2 = 0.f;
-                if (valid) {
-                    st4_hint(p.x_out + (size_t)(p.row_offset + n) * DP + 4 * lig, xn, stream_pol);
-                    if (p.n_peers > 1) store_to_peers(p, n, 4 * lig, xn);
-                    if (p.bn_train) {
-                        bn_s1[0] += xn.x; bn_s1[1] += xn.y; bn_s1[2] += xn.z; bn_s1[3] += xn.w;
-                        bn_s2[0] += (double)xn.x * xn.x; bn_s2[1] += (double)xn.y * xn.y;
-                        bn_s2[2] += (double)xn.z * xn.z; bn_s2[3] += (double)xn.w * xn.w;
-                    } else {
-                        const float4 xo = ld4(tb + i * SA + 4 * lig);
-                        const float dx = xn.x - xo.x, dy = xn.y - xo.y, dz = xn.z - xo.z, dw = xn.w - xo.w;
-                        d2 = dx * dx + dy * dy + dz * dz + dw * dw;
-                        o2 = xo.x * xo.x + xo.y * xo.y + xo.z * xo.z + xo.w * xo.w;
+                    for (int c = 0; c < 4; ++c) {
+                        float y = act_apply(act, acc[i][c] + bb[c]);
+                        if (affine) y = fmaf(aa[c], y, cc[c]);
+                        v[c] = (4 * cg + c < D) ? y : 0.f;
                     }
-                }
-                if (!p.bn_train) {
-#pragma unroll
-                    for (int off = LPN / 2; off > 0; off >>= 1) {
-                        d2 += __shfl_xor_sync(0xffffffffu, d2, off);
-                        o2 += __shfl_xor_sync(0xffffffffu, o2, off);
+                    const float4 xn = make_float4(v[0], v[1], v[2], v[3]);
+                    float d2 = 0.f, o2 = 0.f;
+                    if (valid) {
+                        st4_hint(p.x_out + (size_t)(p.row_offset + n) * DP + 4 * cg, xn, stream_pol);
+                        if (p.n_peers > 1) store_to_peers(p, n, 4 * cg, xn);
+                        if (p.bn_train) {
+                            bn_s1[0] += xn.x; bn_s1[1] += xn.y; bn_s1[2] += xn.z; bn_s1[3] += xn.w;
+                            bn_s2[0] += (double)xn.x * xn.x; bn_s2[1] += (double)xn.y * xn.y;
+                            bn_s2[2] += (double)xn.z * xn.z; bn_s2[3] += (double)xn.w * xn.w;
+                        } else {
+                            const float4 xo = ld4(tb + row * SA + 4 * cg);
+                            const float dx = xn.x - xo.x, dy = xn.y - xo.y, dz = xn.z - xo.z, dw = xn.w - xo.w;
+                            d2 = dx * dx + dy * dy + dz * dz + dw * dw;
+                            o2 = xo.x * xo.x + xo.y * xo.y + xo.z * xo.z + xo.w * xo.w;
+                        }
                     }
-                    any_moving |= valid && (sqrtf(d2) > p.thr * sqrtf(o2));
+                    if (!p.bn_train) {
+#pragma unroll
+                        for (int off = CG / 2; off > 0; off >>= 1) {
+                            d2 += __shfl_xor_sync(0xffffffffu, d2, off);
+                            o2 += __shfl_xor_sync(0xffffffffu, o2, off);
+                        }
+                        any_moving |= valid && (sqrtf(d2) > p.thr * sqrtf(o2));
+                    }
                 }
             }
             if (tile + 2 * stride < ntiles) {   // this buffer's next tile: fetch its own rows, then hand the buffer back
