@@ -152,6 +152,14 @@ __device__ __forceinline__ void store_to_peers(const IterParams& p, long long lo
         if (r < p.n_peers && r != p.rank && ((need >> r) & 1u)) *reinterpret_cast<float4*>(p.peer_out[r] + off) = v;
 }
 
+__device__ __forceinline__ void store_pair_to_peers(const IterParams& p, long long local_row, int col, float y0, float y1) {
+    const uint32_t need = p.peer_mask ? __ldg(p.peer_mask + local_row) : 0xffffffffu;
+    const size_t off = (size_t)(p.row_offset + local_row) * (size_t)p.net.DP + col;
+#pragma unroll
+    for (int r = 0; r < GNN_MAX_PEERS; ++r)
+        if (r < p.n_peers && r != p.rank && ((need >> r) & 1u)) *reinterpret_cast<float2*>(p.peer_out[r] + off) = make_float2(y0, y1);
+}
+
 __device__ __forceinline__ float drop1(float v, bool active, uint32_t key, uint64_t idx, float rate, float scale) {
     if (!active) return v;
     return dropout_keep(key, idx, rate) ? v * scale : 0.f;

@@ -35,6 +35,19 @@ __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) 
 template <int N>
 __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
+// D (16x8, fp32) += A (16x8, tf32, row) * B (8x8, tf32, col): the legacy warp-level tensor-core path of sm_100a
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+// x = hi + lo with hi exactly representable in tf32 (low 13 mantissa bits cleared): the 3-pass split that keeps the
+// product at fp32 accuracy (hi*hi + hi*lo + lo*hi; the dropped lo*lo term is ~2^-20 relative)
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+    hi = __float_as_uint(x) & 0xffffe000u;
+    lo = __float_as_uint(x - __uint_as_float(hi));
+}
+
 constexpr int WS_TN = 64;          // nodes per tile
 constexpr int WS_MLP = 128;        // threads of ONE MLP group (4 warps); two groups: even / odd tiles
 constexpr int WS_MLP_ALL = 256;    // both MLP groups (warps 0-7)
@@ -42,9 +55,12 @@ constexpr int WS_GATHER = 256;     // gather threads (warps 8-15)
 constexpr int WS_THREADS = 512;
 constexpr int WS_PAIR = WS_MLP + WS_GATHER;   // participants of a FULL / EMPTY barrier: one MLP group + the gather warps
 
+// weights in shared memory: the Dense kernel in mma B-fragment order (K padded to a multiple of 8), bias, affine a / c
+static inline size_t ws_weight_floats(const NetLayout& lay) { return (size_t)((lay.KP + 7) / 8) * 8 * lay.DP + 3 * (size_t)lay.DP; }
+
 // shared-memory footprint (bytes) for a landing capacity of `cap` rows per stage
 static inline size_t ws_smem_bytes(const NetLayout& lay, int cap, bool has_val) {
-    size_t fl = (size_t)lay.fwd_floats + 2 * (size_t)WS_TN * lay.SA + 2 * (size_t)cap * lay.DP + 4 * 68 + 4 * WS_TN +
+    size_t fl = ws_weight_floats(lay) + 2 * (size_t)WS_TN * lay.SA + 2 * (size_t)cap * lay.DP + 4 * 68 + 4 * WS_TN +
                 3 * (size_t)cap * (has_val ? 2 : 1);   // tiles x2, landing x2, row pointers / scales x4, arc indices x3
     return fl * 4;
 }
@@ -56,7 +72,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) state_iter_ws_kernel(const Iter
     constexpr int NPG = TN / NGRP;        // consecutive nodes per lane group
     static_assert(NPG >= 1 && NGRP * NPG == TN, "lane mapping");
     constexpr int NG = TN / 4;            // MLP micro-tiles: 4 nodes (ng + NG*i) x 4 units
-    static_assert(NG * (DP / 4) <= WS_MLP, "one micro-tile per MLP thread (in-place output)");
+    static_assert(DP % 8 == 0 && TN == 64, "4 MLP warps x 16 nodes, DP / 8 accumulator fragments each");
 
     if (*reinterpret_cast<const volatile int*>(p.go_cur) == 0) return;
 
@@ -65,8 +81,12 @@ __global__ void __launch_bounds__(WS_THREADS, 1) state_iter_ws_kernel(const Iter
     const int SA = net.SA, CP = net.CP, KP = net.KP, cap = p.scol_cap;
 
     extern __shared__ __align__(16) float smem[];
-    float* sW = smem;
-    float* tile0 = sW + net.fwd_floats;                 // [2][TN][SA]
+    constexpr int NT8 = DP / 8;
+    const int KS = (KP + 7) / 8;
+    float* sW = smem;                                   // [KS][NT8][32 lanes][2]: B fragments of the Dense kernel
+    float* sBias = sW + KS * 8 * DP;                    // [DP]
+    float* sAff = sBias + DP;                           // a[DP], c[DP]
+    float* tile0 = sAff + 2 * DP;                       // [2][TN][SA]
     float* land0 = tile0 + 2 * TN * SA;                 // [2][cap][DP]
     int* srow0 = reinterpret_cast<int*>(land0 + 2 * (size_t)cap * DP);   // [4][68]
     float* sscale0 = reinterpret_cast<float*>(srow0 + 4 * 68);           // [4][TN]
@@ -74,7 +94,18 @@ __global__ void __launch_bounds__(WS_THREADS, 1) state_iter_ws_kernel(const Iter
     float* sval0 = reinterpret_cast<float*>(scol0 + 3 * cap);            // [3][cap] (HAS_VAL)
     __shared__ int s_flag;
 
-    for (int i = tid * 4; i < net.fwd_floats; i += WS_THREADS * 4) st4(sW + i, ldg4(p.wpack + i));
+    // the Dense kernel in mma B-fragment order:
+    //   sW[((ks * NT8 + nt) * 32 + lane) * 2 + h] = W[8 ks + (lane & 3) + 4 h][8 nt + (lane >> 2)]   (0 beyond KP)
+    for (int i = tid; i < KS * NT8 * 64; i += WS_THREADS) {
+        const int h = i & 1, lane = (i >> 1) & 31, nt = (i >> 6) % NT8, ks = (i >> 6) / NT8;
+        const int k = 8 * ks + (lane & 3) + 4 * h, n = 8 * nt + (lane >> 2);
+        sW[i] = k < KP ? __ldg(p.wpack + net.w_off[0] + k * DP + n) : 0.f;
+    }
+    for (int i = tid; i < DP; i += WS_THREADS) {
+        sBias[i] = __ldg(p.wpack + net.b_off[0] + i);
+        sAff[i] = __ldg(p.wpack + net.aff_off + i);
+        sAff[DP + i] = __ldg(p.wpack + net.aff_off + DP + i);
+    }
     if (tid == 0) s_flag = 0;
     __syncthreads();
 
@@ -226,22 +257,22 @@ __global__ void __launch_bounds__(WS_THREADS, 1) state_iter_ws_kernel(const Iter
         cp_async_wait_group<0>();
     } else {
         // ============================================= MLP WARPS ==============================================
-        // two MLP groups of 4 warps: group g takes the tiles with sequence number it = g, g+2, ... (= tile buffer g)
+        // two MLP groups of 4 warps: group g takes the tiles with sequence number it = g, g+2, ... (= tile buffer g).
+        // Inside a group warp w owns nodes [16 w, 16 w + 16) of the tile and all DP outputs: NT8 accumulator fragments
         constexpr int CG = DP / 4;
         const int mgroup = tid / WS_MLP, mt = tid % WS_MLP;
-        const int cg = mt % CG, ng = mt / CG;
-        const bool has_item = mt < NG * CG;
+        const int mwarp = mt >> 5, lane = mt & 31, fg = lane >> 2, ft = lane & 3;   // fragment coordinates (groupID, thread-in-group)
         const int lig = mt % LPN;
-        const float* W = sW + net.w_off[0];
-        const float* bias = sW + net.b_off[0];
-        const float* aff_a = sW + net.aff_off;
-        const float* aff_c = aff_a + DP;
+        const float* bias = sBias;
+        const float* aff_a = sAff;
+        const float* aff_c = sAff + DP;
         const int act = net.act[0], D = net.D;
         const bool affine = !p.bn_train;
         const uint64_t stream_pol = l2_policy_evict_first();
-        double bn_s1[4] = {0., 0., 0., 0.}, bn_s2[4] = {0., 0., 0., 0.};
+        double bn_s1[2 * NT8], bn_s2[2 * NT8];
+#pragma unroll
+        for (int c = 0; c < 2 * NT8; ++c) bn_s1[c] = bn_s2[c] = 0.;
         bool any_moving = false;
-
         // own state rows and constant rows of a tile -> this group's tile buffer (asynchronous; the gather warps only
         // write the aggregate columns, so the two never touch the same bytes)
         float* tb = tile0 + (size_t)mgroup * TN * SA;
@@ -273,73 +304,88 @@ __global__ void __launch_bounds__(WS_THREADS, 1) state_iter_ws_kernel(const Iter
             cp_async_wait_group<0>();                              // my own / constant rows too ...
             named_bar_sync(GNN_BAR_MLP0 + mgroup, WS_MLP);         // ... and those of the rest of the group
 
-            // Dense layer: 4 nodes x 4 units per thread, k unrolled by 8
-            float acc[4][4];
+            // Dense layer on the tensor cores: 16 x DP outputs per warp, K in steps of 8, 3 x TF32 (fp32-accurate)
+            float acc[NT8][4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
-            if (has_item) {
-                const float* inb = tb + ng * SA;
-                const float* wb = W + 4 * cg;
-#pragma unroll 2
-                for (int k = 0; k < KP; k += 4) {
-                    const float4 w0 = ld4(wb + (k + 0) * DP), w1 = ld4(wb + (k + 1) * DP);
-                    const float4 w2 = ld4(wb + (k + 2) * DP), w3 = ld4(wb + (k + 3) * DP);
+            for (int nt = 0; nt < NT8; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+            {
+                const float* arow0 = tb + (16 * mwarp + fg) * SA + ft;       // rows fg and fg + 8 of this warp's block
+                const float* arow1 = arow0 + 8 * SA;
+                const float2* wf = reinterpret_cast<const float2*>(sW) + lane;
+#pragma unroll 3
+                for (int ks = 0; ks < KS; ++ks) {
+                    const int k0 = 8 * ks + ft;
+                    const bool in0 = k0 < KP, in1 = k0 + 4 < KP;             // K padded to a multiple of 8: no read past the inputs
+                    uint32_t ahi[4], alo[4];
+                    split_tf32(in0 ? arow0[8 * ks] : 0.f, ahi[0], alo[0]);
+                    split_tf32(in0 ? arow1[8 * ks] : 0.f, ahi[1], alo[1]);
+                    split_tf32(in1 ? arow0[8 * ks + 4] : 0.f, ahi[2], alo[2]);
+                    split_tf32(in1 ? arow1[8 * ks + 4] : 0.f, ahi[3], alo[3]);
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const float4 a = ld4(inb + i * NG * SA + k);
-                        acc[i][0] = fmaf(a.x, w0.x, acc[i][0]); acc[i][1] = fmaf(a.x, w0.y, acc[i][1]);
-                        acc[i][2] = fmaf(a.x, w0.z, acc[i][2]); acc[i][3] = fmaf(a.x, w0.w, acc[i][3]);
-                        acc[i][0] = fmaf(a.y, w1.x, acc[i][0]); acc[i][1] = fmaf(a.y, w1.y, acc[i][1]);
-                        acc[i][2] = fmaf(a.y, w1.z, acc[i][2]); acc[i][3] = fmaf(a.y, w1.w, acc[i][3]);
-                        acc[i][0] = fmaf(a.z, w2.x, acc[i][0]); acc[i][1] = fmaf(a.z, w2.y, acc[i][1]);
-                        acc[i][2] = fmaf(a.z, w2.z, acc[i][2]); acc[i][3] = fmaf(a.z, w2.w, acc[i][3]);
-                        acc[i][0] = fmaf(a.w, w3.x, acc[i][0]); acc[i][1] = fmaf(a.w, w3.y, acc[i][1]);
-                        acc[i][2] = fmaf(a.w, w3.z, acc[i][2]); acc[i][3] = fmaf(a.w, w3.w, acc[i][3]);
+                    for (int nt = 0; nt < NT8; ++nt) {
+                        const float2 w2 = wf[(ks * NT8 + nt) * 32];
+                        uint32_t bhi[2], blo[2];
+                        split_tf32(w2.x, bhi[0], blo[0]);
+                        split_tf32(w2.y, bhi[1], blo[1]);
+                        mma_tf32_16x8x8(acc[nt], alo, bhi);
+                        mma_tf32_16x8x8(acc[nt], ahi, blo);
+                        mma_tf32_16x8x8(acc[nt], ahi, bhi);
                     }
                 }
             }
-            // epilogue straight from the accumulators: bias + activation + affine, 128-bit store of the new state (8 lanes
-            // = one 128-byte row), convergence test reduced over the CG lanes that share a node
-            if (has_item) {
-                const float4 b4 = ld4(bias + 4 * cg), a4 = ld4(aff_a + 4 * cg), c4 = ld4(aff_c + 4 * cg);
-                const float bb[4] = {b4.x, b4.y, b4.z, b4.w}, aa[4] = {a4.x, a4.y, a4.z, a4.w}, cc[4] = {c4.x, c4.y, c4.z, c4.w};
+
+            // epilogue straight from the accumulator fragments: bias + activation + affine, 8-byte stores (4 lanes = one
+            // 32-byte sector), convergence test reduced over the 4 lanes that share a node row.  The activation is a
+            // compile-time constant inside (one uniform switch per tile instead of one per element)
+            auto epilogue = [&](auto act_c) {
+                constexpr int ACT = decltype(act_c)::value;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int row = ng + NG * i;
+                for (int half = 0; half < 2; ++half) {
+                    const int row = 16 * mwarp + fg + 8 * half;
                     const long long n = n0 + row;
                     const bool valid = row < nvalid;
-                    float v[4];
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        float y = act_apply(act, acc[i][c] + bb[c]);
-                        if (affine) y = fmaf(aa[c], y, cc[c]);
-                        v[c] = (4 * cg + c < D) ? y : 0.f;
-                    }
-                    const float4 xn = make_float4(v[0], v[1], v[2], v[3]);
                     float d2 = 0.f, o2 = 0.f;
-                    if (valid) {
-                        st4_hint(p.x_out + (size_t)(p.row_offset + n) * DP + 4 * cg, xn, stream_pol);
-                        if (p.n_peers > 1) store_to_peers(p, n, 4 * cg, xn);
-                        if (p.bn_train) {
-                            bn_s1[0] += xn.x; bn_s1[1] += xn.y; bn_s1[2] += xn.z; bn_s1[3] += xn.w;
-                            bn_s2[0] += (double)xn.x * xn.x; bn_s2[1] += (double)xn.y * xn.y;
-                            bn_s2[2] += (double)xn.z * xn.z; bn_s2[3] += (double)xn.w * xn.w;
-                        } else {
-                            const float4 xo = ld4(tb + row * SA + 4 * cg);
-                            const float dx = xn.x - xo.x, dy = xn.y - xo.y, dz = xn.z - xo.z, dw = xn.w - xo.w;
-                            d2 = dx * dx + dy * dy + dz * dz + dw * dw;
-                            o2 = xo.x * xo.x + xo.y * xo.y + xo.z * xo.z + xo.w * xo.w;
+#pragma unroll
+                    for (int nt = 0; nt < NT8; ++nt) {
+                        const int j0 = 8 * nt + 2 * ft;
+                        const float2 b2 = *reinterpret_cast<const float2*>(bias + j0);
+                        float y0 = act_apply(ACT, acc[nt][2 * half] + b2.x), y1 = act_apply(ACT, acc[nt][2 * half + 1] + b2.y);
+                        if (affine) {
+                            const float2 a2 = *reinterpret_cast<const float2*>(aff_a + j0), c2 = *reinterpret_cast<const float2*>(aff_c + j0);
+                            y0 = fmaf(a2.x, y0, c2.x); y1 = fmaf(a2.y, y1, c2.y);
+                        }
+                        if (j0 >= D) y0 = 0.f;
+                        if (j0 + 1 >= D) y1 = 0.f;
+                        if (valid) {
+                            float* dstp = p.x_out + (size_t)(p.row_offset + n) * DP + j0;
+                            asm volatile("st.global.L2::cache_hint.v2.f32 [%0], {%1, %2}, %3;" ::"l"(dstp), "f"(y0), "f"(y1), "l"(stream_pol) : "memory");
+                            if (p.n_peers > 1) store_pair_to_peers(p, n, j0, y0, y1);
+                            if (p.bn_train) {
+                                bn_s1[2 * nt] += y0; bn_s1[2 * nt + 1] += y1;
+                                bn_s2[2 * nt] += (double)y0 * y0; bn_s2[2 * nt + 1] += (double)y1 * y1;
+                            } else {
+                                const float2 xo = *reinterpret_cast<const float2*>(tb + row * SA + j0);
+                                const float dx = y0 - xo.x, dy = y1 - xo.y;
+                                d2 += dx * dx + dy * dy;
+                                o2 += xo.x * xo.x + xo.y * xo.y;
+                            }
                         }
                     }
                     if (!p.bn_train) {
-#pragma unroll
-                        for (int off = CG / 2; off > 0; off >>= 1) {
-                            d2 += __shfl_xor_sync(0xffffffffu, d2, off);
-                            o2 += __shfl_xor_sync(0xffffffffu, o2, off);
-                        }
+                        d2 += __shfl_xor_sync(0xffffffffu, d2, 1); o2 += __shfl_xor_sync(0xffffffffu, o2, 1);
+                        d2 += __shfl_xor_sync(0xffffffffu, d2, 2); o2 += __shfl_xor_sync(0xffffffffu, o2, 2);
                         any_moving |= valid && (sqrtf(d2) > p.thr * sqrtf(o2));
                     }
                 }
+            };
+            switch (act) {
+                case GNN_ACT_RELU: epilogue(std::integral_constant<int, GNN_ACT_RELU>{}); break;
+                case GNN_ACT_TANH: epilogue(std::integral_constant<int, GNN_ACT_TANH>{}); break;
+                case GNN_ACT_SIGMOID: epilogue(std::integral_constant<int, GNN_ACT_SIGMOID>{}); break;
+                case GNN_ACT_SELU: epilogue(std::integral_constant<int, GNN_ACT_SELU>{}); break;
+                case GNN_ACT_ELU: epilogue(std::integral_constant<int, GNN_ACT_ELU>{}); break;
+                case GNN_ACT_SOFTPLUS: epilogue(std::integral_constant<int, GNN_ACT_SOFTPLUS>{}); break;
+                default: epilogue(std::integral_constant<int, GNN_ACT_LINEAR>{}); break;
             }
             if (tile + 2 * stride < ntiles) {   // this buffer's next tile: fetch its own rows, then hand the buffer back
                 named_bar_sync(GNN_BAR_MLP0 + mgroup, WS_MLP);   // the whole group has finished reading the tile
@@ -350,28 +396,28 @@ __global__ void __launch_bounds__(WS_THREADS, 1) state_iter_ws_kernel(const Iter
         }
 
         if (p.bn_train) {
+            // lanes with the same ft hold the same columns: reduce over fg (xor 4, 8, 16), then over the 8 MLP warps
 #pragma unroll
-            for (int c = 0; c < 4; ++c)
-                for (int off = LPN; off < 32; off <<= 1) {
+            for (int c = 0; c < 2 * NT8; ++c)
+                for (int off = 4; off < 32; off <<= 1) {
                     bn_s1[c] += __shfl_xor_sync(0xffffffffu, bn_s1[c], off);
                     bn_s2[c] += __shfl_xor_sync(0xffffffffu, bn_s2[c], off);
                 }
-            // the landing zones are idle for the MLP warps' purposes only after the gather warps are done: use a private
-            // static buffer instead (4 warps x LPN lanes x 8 doubles)
-            __shared__ double red[8 * 8 * 8];
-            const int warp = tid >> 5, lane = tid & 31;
-            if (lane < LPN)
+            __shared__ double red[8][2][DP];
+            const int warp = tid >> 5;
+            if (lane < 4)
 #pragma unroll
-                for (int c = 0; c < 4; ++c) { red[(warp * LPN + lane) * 8 + c] = bn_s1[c]; red[(warp * LPN + lane) * 8 + 4 + c] = bn_s2[c]; }
+                for (int c = 0; c < 2 * NT8; ++c) {
+                    const int j = 8 * (c >> 1) + 2 * lane + (c & 1);
+                    red[warp][0][j] = bn_s1[c];
+                    red[warp][1][j] = bn_s2[c];
+                }
             named_bar_sync(GNN_BAR_MLP_ALL, WS_MLP_ALL);
-            if (tid < LPN) {
-                double s1[4] = {0., 0., 0., 0.}, s2[4] = {0., 0., 0., 0.};
-                for (int w = 0; w < 8; ++w)
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) { s1[c] += red[(w * LPN + tid) * 8 + c]; s2[c] += red[(w * LPN + tid) * 8 + 4 + c]; }
-                double* dst = p.bn_partial + (size_t)blockIdx.x * 2 * DP;
-#pragma unroll
-                for (int c = 0; c < 4; ++c) { dst[4 * tid + c] = s1[c]; dst[DP + 4 * tid + c] = s2[c]; }
+            if (tid < 2 * DP) {
+                const int which = tid / DP, j = tid % DP;
+                double sum = 0.;
+                for (int w = 0; w < 8; ++w) sum += red[w][which][j];
+                p.bn_partial[(size_t)blockIdx.x * 2 * DP + which * DP + j] = sum;
             }
         } else {
             if (p.go_next && __any_sync(0xffffffffu, any_moving) && (tid & 31) == 0) s_flag = 1;

@@ -204,8 +204,8 @@ int make_plan(const gnn_graph* g, const gnn_mlp* net, const gnn_loop_args* a, Pl
         // landing capacity: the average tile + 25 %, bounded by what one CTA per SM can hold
         const long long avg = g->n_nodes > 0 ? (g->n_arcs * WS_TN) / g->n_nodes : 0;
         int cap = (int)std::min<long long>(4096, std::max<long long>(64, (avg * 5 / 4 + 15) / 16 * 16));
-        while (cap > 16 && ws_smem_bytes(lay, cap, plan->has_val) + 4096 > (size_t)di.smem_optin) cap -= 16;
-        if (ws_smem_bytes(lay, cap, plan->has_val) + 4096 <= (size_t)di.smem_optin) {
+        while (cap > 16 && ws_smem_bytes(lay, cap, plan->has_val) + 4608 > (size_t)di.smem_optin) cap -= 16;
+        if (ws_smem_bytes(lay, cap, plan->has_val) + 4608 <= (size_t)di.smem_optin) {
             plan->ws = true;
             plan->kernel = ks->iter_ws[plan->has_val ? 1 : 0];
             plan->ts = TileShape{WS_TN, WS_THREADS};

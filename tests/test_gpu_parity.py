@@ -327,8 +327,8 @@ def test_ws_kernel_forward_and_training(name, monkeypatch):
     assert_parity(got, want, want64=lambda: run_oracle(case, training=True, float64=True))
 
 
-def test_ws_and_symmetric_kernels_agree_bitwise(monkeypatch):
-    """ both kernels sum the arcs in stored order and use the same FMA order per output: identical states """
+def test_ws_and_symmetric_kernels_agree(monkeypatch):
+    """ both kernels sum the arcs in stored order; the MLP differs only in rounding (tensor-core 3xTF32 vs fp32 FMA) """
     _require_gpu()
     case = random_case(seed=710, n_nodes=30000, n_arcs=240000, NL=3, AL=1, DS=32, act='selu', max_iter=5, threshold=0.0, bn=True)
     monkeypatch.setenv('GNN_B200_KERNEL', 'ws')
@@ -336,4 +336,4 @@ def test_ws_and_symmetric_kernels_agree_bitwise(monkeypatch):
     monkeypatch.setenv('GNN_B200_KERNEL', 'sym')
     b = run_cuda(case, training=False)
     assert a['k'] == b['k']
-    assert rel_err(a['state'], b['state']) < 1e-6
+    assert rel_err(a["state"], b["state"]) < 2e-5   # 3xTF32 tensor-core product vs sequential fp32 FMA
