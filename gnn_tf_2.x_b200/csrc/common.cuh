@@ -60,18 +60,33 @@ static inline int next_pow2(int v) {
 // Activations. exp / division use the hardware approximations (ex2.approx, rcp.approx: ~2 ulp): the ABSOLUTE error
 // stays near 1e-7, far inside the 1e-4 parity tolerance, and the element-wise pass stays a handful of instructions.
 // selu / elu follow TensorFlow's own formula exp(z) - 1.
+// e^x as one MUFU: ex2.approx.ftz(x * log2(e)).  Results below 2^-126 flush to zero (irrelevant for every use below).
+__device__ __forceinline__ float fast_exp(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
+    return y;
+}
+
+// Branch-free on purpose (select, not if/else): the element-wise epilogues keep many independent elements in flight.
 __device__ __forceinline__ float act_apply(int act, float z) {
     switch (act) {
         case GNN_ACT_RELU: return fmaxf(z, 0.f);
         case GNN_ACT_TANH: {
             const float a = fminf(fabsf(z), 15.f);          // tanh(15) == 1 in fp32
-            const float e = __expf(2.f * a);
+            const float e = fast_exp(2.f * a);
             return copysignf(1.f - __fdividef(2.f, e + 1.f), z);
         }
-        case GNN_ACT_SIGMOID: return __fdividef(1.f, 1.f + __expf(-z));
-        case GNN_ACT_SELU: return z > 0.f ? SELU_SCALE * z : (SELU_SCALE * SELU_ALPHA) * (__expf(z) - 1.f);
-        case GNN_ACT_ELU: return z > 0.f ? z : __expf(z) - 1.f;
-        case GNN_ACT_SOFTPLUS: return z > 15.f ? z : __logf(1.f + __expf(z));
+        case GNN_ACT_SIGMOID: return __fdividef(1.f, 1.f + fast_exp(-z));
+        case GNN_ACT_SELU: {
+            const float neg = fmaf(SELU_SCALE * SELU_ALPHA, fast_exp(fminf(z, 0.f)), -(SELU_SCALE * SELU_ALPHA));
+            const float pos = SELU_SCALE * z;
+            return z > 0.f ? pos : neg;
+        }
+        case GNN_ACT_ELU: {
+            const float neg = fast_exp(fminf(z, 0.f)) - 1.f;
+            return z > 0.f ? z : neg;
+        }
+        case GNN_ACT_SOFTPLUS: return z > 15.f ? z : __logf(1.f + fast_exp(fminf(z, 15.f)));
         default: return z;  // linear (softmax is handled row-wise by its caller)
     }
 }

@@ -339,42 +339,80 @@ __global__ void __launch_bounds__(WS_THREADS, 1) state_iter_ws_kernel(const Iter
             // compile-time constant inside (one uniform switch per tile instead of one per element)
             auto epilogue = [&](auto act_c) {
                 constexpr int ACT = decltype(act_c)::value;
+                // 1. new state values in place (element-wise, no branches inside: 4 * NT8 independent chains)
 #pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    const int row = 16 * mwarp + fg + 8 * half;
-                    const long long n = n0 + row;
-                    const bool valid = row < nvalid;
-                    float d2 = 0.f, o2 = 0.f;
+                for (int nt = 0; nt < NT8; ++nt) {
+                    const float2 b2 = *reinterpret_cast<const float2*>(bias + 8 * nt + 2 * ft);
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        acc[nt][2 * half] = act_apply(ACT, acc[nt][2 * half] + b2.x);
+                        acc[nt][2 * half + 1] = act_apply(ACT, acc[nt][2 * half + 1] + b2.y);
+                    }
+                }
+                if (affine) {
+#pragma unroll
+                    for (int nt = 0; nt < NT8; ++nt) {
+                        const float2 a2 = *reinterpret_cast<const float2*>(aff_a + 8 * nt + 2 * ft);
+                        const float2 c2 = *reinterpret_cast<const float2*>(aff_c + 8 * nt + 2 * ft);
+#pragma unroll
+                        for (int half = 0; half < 2; ++half) {
+                            acc[nt][2 * half] = fmaf(a2.x, acc[nt][2 * half], c2.x);
+                            acc[nt][2 * half + 1] = fmaf(a2.y, acc[nt][2 * half + 1], c2.y);
+                        }
+                    }
+                }
+                if (D < DP) {   // padding columns stay zero
 #pragma unroll
                     for (int nt = 0; nt < NT8; ++nt) {
                         const int j0 = 8 * nt + 2 * ft;
-                        const float2 b2 = *reinterpret_cast<const float2*>(bias + j0);
-                        float y0 = act_apply(ACT, acc[nt][2 * half] + b2.x), y1 = act_apply(ACT, acc[nt][2 * half + 1] + b2.y);
-                        if (affine) {
-                            const float2 a2 = *reinterpret_cast<const float2*>(aff_a + j0), c2 = *reinterpret_cast<const float2*>(aff_c + j0);
-                            y0 = fmaf(a2.x, y0, c2.x); y1 = fmaf(a2.y, y1, c2.y);
-                        }
-                        if (j0 >= D) y0 = 0.f;
-                        if (j0 + 1 >= D) y1 = 0.f;
-                        if (valid) {
-                            float* dstp = p.x_out + (size_t)(p.row_offset + n) * DP + j0;
-                            asm volatile("st.global.L2::cache_hint.v2.f32 [%0], {%1, %2}, %3;" ::"l"(dstp), "f"(y0), "f"(y1), "l"(stream_pol) : "memory");
-                            if (p.n_peers > 1) store_pair_to_peers(p, n, j0, y0, y1);
-                            if (p.bn_train) {
-                                bn_s1[2 * nt] += y0; bn_s1[2 * nt + 1] += y1;
-                                bn_s2[2 * nt] += (double)y0 * y0; bn_s2[2 * nt + 1] += (double)y1 * y1;
-                            } else {
-                                const float2 xo = *reinterpret_cast<const float2*>(tb + row * SA + j0);
-                                const float dx = y0 - xo.x, dy = y1 - xo.y;
-                                d2 += dx * dx + dy * dy;
-                                o2 += xo.x * xo.x + xo.y * xo.y;
-                            }
+#pragma unroll
+                        for (int half = 0; half < 2; ++half) {
+                            if (j0 >= D) acc[nt][2 * half] = 0.f;
+                            if (j0 + 1 >= D) acc[nt][2 * half + 1] = 0.f;
                         }
                     }
-                    if (!p.bn_train) {
+                }
+                // 2. stores: 8 bytes per lane, 4 lanes = one 32-byte sector
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    const int row = 16 * mwarp + fg + 8 * half;
+                    if (row < nvalid) {
+                        float* orow = p.x_out + (size_t)(p.row_offset + n0 + row) * DP + 2 * ft;
+#pragma unroll
+                        for (int nt = 0; nt < NT8; ++nt)
+                            asm volatile("st.global.L2::cache_hint.v2.f32 [%0], {%1, %2}, %3;" ::"l"(orow + 8 * nt), "f"(acc[nt][2 * half]),
+                                         "f"(acc[nt][2 * half + 1]), "l"(stream_pol) : "memory");
+                        if (p.n_peers > 1)
+#pragma unroll
+                            for (int nt = 0; nt < NT8; ++nt) store_pair_to_peers(p, n0 + row, 8 * nt + 2 * ft, acc[nt][2 * half], acc[nt][2 * half + 1]);
+                    }
+                }
+                // 3. BatchNormalization batch statistics (training) or the convergence test against the old state in the tile
+                if (p.bn_train) {
+#pragma unroll
+                    for (int half = 0; half < 2; ++half)
+                        if (16 * mwarp + fg + 8 * half < nvalid)
+#pragma unroll
+                            for (int nt = 0; nt < NT8; ++nt) {
+                                const float y0 = acc[nt][2 * half], y1 = acc[nt][2 * half + 1];
+                                bn_s1[2 * nt] += y0; bn_s1[2 * nt + 1] += y1;
+                                bn_s2[2 * nt] += (double)y0 * y0; bn_s2[2 * nt + 1] += (double)y1 * y1;
+                            }
+                } else {
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        const int row = 16 * mwarp + fg + 8 * half;
+                        float d2 = 0.f, o2 = 0.f;
+#pragma unroll
+                        for (int nt = 0; nt < NT8; ++nt) {
+                            const float2 xo = *reinterpret_cast<const float2*>(tb + row * SA + 8 * nt + 2 * ft);
+                            const float dx = acc[nt][2 * half] - xo.x, dy = acc[nt][2 * half + 1] - xo.y;
+                            d2 += dx * dx + dy * dy;
+                            o2 += xo.x * xo.x + xo.y * xo.y;
+                        }
                         d2 += __shfl_xor_sync(0xffffffffu, d2, 1); o2 += __shfl_xor_sync(0xffffffffu, o2, 1);
                         d2 += __shfl_xor_sync(0xffffffffu, d2, 2); o2 += __shfl_xor_sync(0xffffffffu, o2, 2);
-                        any_moving |= valid && (sqrtf(d2) > p.thr * sqrtf(o2));
+                        any_moving |= (row < nvalid) && (sqrtf(d2) > p.thr * sqrtf(o2));
                     }
                 }
             };
