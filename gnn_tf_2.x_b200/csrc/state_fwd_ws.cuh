@@ -1,26 +1,30 @@
 // state_fwd_ws.cuh -- warp-specialised, software-pipelined variant of the fused forward iteration kernel.
 //
-// Why: the gather of a uniform-random graph is latency bound.  A gather-only microbenchmark on B200
-// (scripts/gather_microbench.cu) needs >= 1000 128-byte rows in flight per SM to reach the L2/HBM limit; the symmetric
-// kernel (state_fwd.cuh) holds its rows in registers and cannot have that many in flight next to the MLP.  Here the
-// rows land in shared memory through cp.async (no registers, deep queue) and two warp groups run concurrently:
+// Why: the gather of a uniform-random graph is bound by how many 128-byte rows an SM keeps in flight.  A gather-only
+// microbenchmark on B200 (scripts/gather_microbench.cu) needs >= 1000 rows in flight per SM to reach the L2/HBM limit;
+// the symmetric kernel (state_fwd.cuh) holds its rows in registers and cannot have that many in flight next to the MLP.
+// Here the rows land in shared memory through cp.async (no registers, deep queue) and THREE roles run concurrently in
+// one persistent CTA of 512 threads per SM (64-node tiles, double-buffered tiles and landing zones):
 //
-//   gather warps (4): for tile j+1: stage row pointers / arc indices -> cp.async every source row into landing[(j+1)&1],
-//                     own rows and constant rows straight into tile[(j+1)&1];  for tile j: wait for its rows, segment-sum
-//                     them out of shared memory in stored order (deterministic, no atomics) into tile[j&1]  -> FULL[j&1]
-//   MLP warps    (4): wait FULL[j&1] -> Dense layer as register-blocked FMA tiles (4 nodes x 4 units per thread, weights in
-//                     shared memory) -> bias / activation / affine -> 128-bit coalesced store of the new state +
-//                     convergence test (+ BatchNormalization batch statistics when training)          -> EMPTY[j&1]
+//   issue warps   (4): never wait for data.  Per tile: arc sources / row pointers of tile j+2 -> shared memory
+//                      (cp.async, completion -> mbarrier COLS), then one 16-byte cp.async per lane for every source row
+//                      of tile j -> landing[j&1]; completion of all of them arrives on mbarrier LANDED[j&1]
+//                      (cp.async.mbarrier.arrive.noinc).  They block only on the LSU queue, i.e. the memory pipe is fed
+//                      continuously -- the issue loop alone runs at the gather floor of the microbenchmark.
+//   consume warps (4): wait LANDED[j&1] -> segment sums out of shared memory in stored order (deterministic, no
+//                      atomics) into tile[j&1]  -> FULL[j&1] for the MLP, mbarrier FREE[j&1] for the issue warps
+//   MLP warps     (8): two groups of 4, even / odd tiles.  wait FULL -> Dense layer on the tensor cores (mma.sync
+//                      m16n8k8, 3xTF32 = fp32-accurate) -> bias / activation / affine -> store of the new state +
+//                      convergence test (+ BatchNormalization batch statistics when training)          -> EMPTY[j&1]
 //
-// One persistent CTA of 256 threads per SM, 64-node tiles, double-buffered tiles and landing zones (2 x ~640 rows in
-// flight per SM at the C4 shape).  Used for single-Dense-layer state nets (what the reference builds by default) with
-// padded state width 16..32 and no active dropout; every other case runs the symmetric kernel.
+// Used for single-Dense-layer state nets (what the reference builds by default) with padded state width 16..32 and no
+// active dropout; every other case runs the symmetric kernel.
 #pragma once
 #include "state_fwd.cuh"
 
 namespace gnn {
 
-#define GNN_BAR_GATHER 1
+#define GNN_BAR_ISSUE 1
 #define GNN_BAR_MLP0 2    // +group
 #define GNN_BAR_FULL0 4   // +b
 #define GNN_BAR_EMPTY0 6  // +b
@@ -51,9 +55,30 @@ __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) 
 constexpr int WS_TN = 64;          // nodes per tile
 constexpr int WS_MLP = 128;        // threads of ONE MLP group (4 warps); two groups: even / odd tiles
 constexpr int WS_MLP_ALL = 256;    // both MLP groups (warps 0-7)
-constexpr int WS_GATHER = 256;     // gather threads (warps 8-15)
+constexpr int WS_CONS = 128;       // consume threads (warps 8-11)
+constexpr int WS_ISSUE = 128;      // issue threads (warps 12-15)
 constexpr int WS_THREADS = 512;
-constexpr int WS_PAIR = WS_MLP + WS_GATHER;   // participants of a FULL / EMPTY barrier: one MLP group + the gather warps
+constexpr int WS_PAIR = WS_MLP + WS_CONS;     // participants of a FULL / EMPTY barrier: one MLP group + the consume warps
+
+// mbarrier (shared memory, CTA scope)
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+// arrives (without touching the pending count) once every cp.async this thread has issued so far has completed
+__device__ __forceinline__ void cp_async_mbar_arrive(uint64_t* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const unsigned addr = (unsigned)__cvta_generic_to_shared(bar);
+    uint32_t done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    } while (!done);
+}
 
 // weights in shared memory: the Dense kernel in mma B-fragment order (K padded to a multiple of 8), bias, affine a / c
 static inline size_t ws_weight_floats(const NetLayout& lay) { return (size_t)((lay.KP + 7) / 8) * 8 * lay.DP + 3 * (size_t)lay.DP; }
@@ -61,17 +86,16 @@ static inline size_t ws_weight_floats(const NetLayout& lay) { return (size_t)((l
 // shared-memory footprint (bytes) for a landing capacity of `cap` rows per stage
 static inline size_t ws_smem_bytes(const NetLayout& lay, int cap, bool has_val) {
     size_t fl = ws_weight_floats(lay) + 2 * (size_t)WS_TN * lay.SA + 2 * (size_t)cap * lay.DP + 4 * 68 + 4 * WS_TN +
-                3 * (size_t)cap * (has_val ? 2 : 1);   // tiles x2, landing x2, row pointers / scales x4, arc indices x3
+                3 * (size_t)cap + (has_val ? 4 * (size_t)cap : 0);   // tiles x2, landing x2, row pointers / scales x4, arc indices x3, weights x4
     return fl * 4;
 }
 
 template <int DP, bool HAS_VAL>
 __global__ void __launch_bounds__(WS_THREADS, 1) state_iter_ws_kernel(const IterParams p) {
     constexpr int TN = WS_TN, LPN = DP / 4;
-    constexpr int NGRP = WS_GATHER / LPN; // lane groups among the gather warps
-    constexpr int NPG = TN / NGRP;        // consecutive nodes per lane group
-    static_assert(NPG >= 1 && NGRP * NPG == TN, "lane mapping");
-    constexpr int NG = TN / 4;            // MLP micro-tiles: 4 nodes (ng + NG*i) x 4 units
+    constexpr int NGRP = WS_CONS / LPN;   // lane groups among the consume (and among the issue) warps
+    constexpr int NPG = TN / NGRP;        // consecutive nodes per consume lane group
+    static_assert(NPG >= 1 && NGRP * NPG == TN && WS_CONS == WS_ISSUE, "lane mapping");
     static_assert(DP % 8 == 0 && TN == 64, "4 MLP warps x 16 nodes, DP / 8 accumulator fragments each");
 
     if (*reinterpret_cast<const volatile int*>(p.go_cur) == 0) return;
@@ -91,8 +115,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) state_iter_ws_kernel(const Iter
     int* srow0 = reinterpret_cast<int*>(land0 + 2 * (size_t)cap * DP);   // [4][68]
     float* sscale0 = reinterpret_cast<float*>(srow0 + 4 * 68);           // [4][TN]
     int* scol0 = reinterpret_cast<int*>(sscale0 + 4 * TN);               // [3][cap]
-    float* sval0 = reinterpret_cast<float*>(scol0 + 3 * cap);            // [3][cap] (HAS_VAL)
+    float* sval0 = reinterpret_cast<float*>(scol0 + 3 * cap);            // [4][cap] (HAS_VAL; read by the consume warps)
     __shared__ int s_flag;
+    __shared__ __align__(8) uint64_t bar_landed[2], bar_free[2], bar_cols[3];
 
     // the Dense kernel in mma B-fragment order:
     //   sW[((ks * NT8 + nt) * 32 + lane) * 2 + h] = W[8 ks + (lane & 3) + 4 h][8 nt + (lane >> 2)]   (0 beyond KP)
@@ -106,73 +131,52 @@ __global__ void __launch_bounds__(WS_THREADS, 1) state_iter_ws_kernel(const Iter
         sAff[i] = __ldg(p.wpack + net.aff_off + i);
         sAff[DP + i] = __ldg(p.wpack + net.aff_off + DP + i);
     }
-    if (tid == 0) s_flag = 0;
+    if (tid == 0) {
+        s_flag = 0;
+        for (int i = 0; i < 2; ++i) { mbar_init(&bar_landed[i], WS_ISSUE); mbar_init(&bar_free[i], WS_CONS); }
+        for (int i = 0; i < 3; ++i) mbar_init(&bar_cols[i], WS_ISSUE);
+    }
     __syncthreads();
 
     const long long ntiles = (p.N + TN - 1) / TN;
     const long long first = blockIdx.x, stride = gridDim.x;
-    const bool is_gather = tid >= WS_MLP_ALL;
+    auto tile_at = [&](int seq) { return first + (long long)seq * stride; };
 
-    if (is_gather) {
-        // =========================================== GATHER WARPS ==============================================
-        const int gt = tid - WS_MLP_ALL;
+    if (tid >= WS_MLP_ALL + WS_CONS) {
+        // ============================================ ISSUE WARPS ==============================================
+        const int gt = tid - WS_MLP_ALL - WS_CONS;
         const int grp = gt / LPN, lig = gt % LPN;
         const uint64_t keep = l2_policy_evict_last();
 
-        // Buffers: tiles and landing zones x2 (b = it & 1), arc indices x3 (q3 = seq % 3), row pointers / scales x4 (q4).
-        // row pointers (+ per-node weights) of a tile: asynchronous 4-byte copies, they ride in the row group
-        auto stage_rowptr_async = [&](long long tile, int q4) {
+        // Buffers: landing zones x2 (b = seq & 1), arc indices x3 (seq % 3), row pointers / scales x4 (seq & 3).
+        // arc sources (+ weights), row pointers (+ per-node scales) of tile seq: asynchronous 4-byte copies.  The arc range
+        // [e0, e1) comes from registers (read one iteration earlier straight from global memory).
+        auto request_cols = [&](long long tile, int seq, int e0, int e1) {
             const long long n0 = tile * TN;
-            for (int i = gt; i <= TN; i += WS_GATHER) cp_async4(srow0 + q4 * 68 + i, p.rowptr + min(n0 + i, p.N));
+            const int q4 = seq & 3, q3 = seq % 3;
+            const int ecount = min(e1 - e0, cap);
+            for (int r = gt; r < ecount; r += WS_ISSUE) {
+                cp_async4(scol0 + (size_t)q3 * cap + r, p.col + e0 + r);
+                if (HAS_VAL) cp_async4(sval0 + (size_t)q4 * cap + r, p.val + e0 + r);
+            }
+            for (int i = gt; i <= TN; i += WS_ISSUE) cp_async4(srow0 + q4 * 68 + i, p.rowptr + min(n0 + i, p.N));
             if (!HAS_VAL)
-                for (int i = gt; i < TN; i += WS_GATHER) {
+                for (int i = gt; i < TN; i += WS_ISSUE) {
                     if (n0 + i < p.N) cp_async4(sscale0 + q4 * TN + i, p.cst + (size_t)(n0 + i) * CP + net.C);
                     else sscale0[q4 * TN + i] = 0.f;
                 }
         };
-        // arc sources of a tile: loaded into registers first (so that independent work can overlap the latency) ...
-        constexpr int CREG = 8;
-        int creg[CREG];
-        float vreg[CREG];
-        auto load_cols = [&](int q4) {
-            const int* srow = srow0 + q4 * 68;
-            const int ebase = srow[0];
-            const int ecount = min(srow[TN] - ebase, cap);
-#pragma unroll
-            for (int u = 0; u < CREG; ++u) {
-                const int r = gt + u * WS_GATHER;
-                creg[u] = 0; vreg[u] = 0.f;
-                if (r < ecount) {
-                    creg[u] = __ldg(p.col + ebase + r);
-                    if (HAS_VAL) vreg[u] = __ldg(p.val + ebase + r);
-                }
-            }
-        };
-        // ... and stored to the index buffer afterwards
-        auto store_cols = [&](int q4, int q3) {
-            const int* srow = srow0 + q4 * 68;
-            const int ebase = srow[0];
-            const int ecount = min(srow[TN] - ebase, cap);
-#pragma unroll
-            for (int u = 0; u < CREG; ++u) {
-                const int r = gt + u * WS_GATHER;
-                if (r < ecount) {
-                    scol0[(size_t)q3 * cap + r] = creg[u];
-                    if (HAS_VAL) sval0[(size_t)q3 * cap + r] = vreg[u];
-                }
-            }
-            for (int r = gt + CREG * WS_GATHER; r < ecount; r += WS_GATHER) {   // very dense tiles only
-                scol0[(size_t)q3 * cap + r] = __ldg(p.col + ebase + r);
-                if (HAS_VAL) sval0[(size_t)q3 * cap + r] = __ldg(p.val + ebase + r);
-            }
+        auto tile_arcs = [&](long long tile, int& e0, int& e1) {
+            e0 = __ldg(p.rowptr + tile * TN);
+            e1 = __ldg(p.rowptr + min(tile * TN + TN, p.N));
         };
         // every source row of the tile -> landing zone b (asynchronous, no registers); a lane group takes chunks of 4
         // consecutive arcs so that their 4 indices are one 128-bit shared-memory load
-        auto issue_rows = [&](int q4, int q3, int b) {
-            const int* srow = srow0 + q4 * 68;
+        auto issue_rows = [&](int seq) {
+            const int* srow = srow0 + (seq & 3) * 68;
             const int ecount = min(srow[TN] - srow[0], cap);
-            float* lb = land0 + (size_t)b * cap * DP + 4 * lig;
-            const int* scol = scol0 + (size_t)q3 * cap;
+            float* lb = land0 + (size_t)(seq & 1) * cap * DP + 4 * lig;
+            const int* scol = scol0 + (size_t)(seq % 3) * cap;
             const float* xl = p.x_in + 4 * lig;
             for (int r = 4 * grp; r < ecount; r += 4 * NGRP) {
                 const int4 s4 = *reinterpret_cast<const int4*>(scol + r);   // entries past ecount are never used
@@ -182,15 +186,49 @@ __global__ void __launch_bounds__(WS_THREADS, 1) state_iter_ws_kernel(const Iter
                 if (r + 3 < ecount) cp_async16_hint(lb + (size_t)(r + 3) * DP, xl + (size_t)s4.w * DP, keep);
             }
         };
-        // segment sums of this lane group's NPG nodes out of the landing zone, stored order
-        auto consume = [&](long long tile, int q4, int q3, int b) {
+
+        int e0, e1;
+        for (int sq = 0; sq < 2; ++sq)
+            if (tile_at(sq) < ntiles) {
+                tile_arcs(tile_at(sq), e0, e1);
+                request_cols(tile_at(sq), sq, e0, e1);
+                cp_async_mbar_arrive(&bar_cols[sq]);
+            }
+        if (tile_at(2) < ntiles) tile_arcs(tile_at(2), e0, e1);     // arc range of tile it + 2, one iteration ahead
+        int it = 0;
+        for (long long tile = first; tile < ntiles; tile += stride, ++it) {
+            const int b = it & 1;
+            const long long t2 = tile + 2 * stride, t3 = tile + 3 * stride;
+            named_bar_sync(GNN_BAR_ISSUE, WS_ISSUE);                 // every issue thread is done reading the indices of tile it-1
+            if (it >= 2) mbar_wait(&bar_free[b], ((it >> 1) - 1) & 1);   // tile it-2 is consumed: landing[b], srow[(it+2)&3] are free
+            if (t2 < ntiles) {
+                request_cols(t2, it + 2, e0, e1);
+                cp_async_mbar_arrive(&bar_cols[(it + 2) % 3]);
+            }
+            if (t3 < ntiles) tile_arcs(t3, e0, e1);
+            mbar_wait(&bar_cols[it % 3], (it / 3) & 1);              // indices / row pointers of tile it have landed
+            issue_rows(it);
+            cp_async_mbar_arrive(&bar_landed[b]);
+        }
+        cp_async_wait_group<0>();
+    } else if (tid >= WS_MLP_ALL) {
+        // =========================================== CONSUME WARPS =============================================
+        const int gt = tid - WS_MLP_ALL;
+        const int grp = gt / LPN, lig = gt % LPN;
+        const uint64_t stream_pol = l2_policy_evict_first();
+        int it = 0;
+        for (long long tile = first; tile < ntiles; tile += stride, ++it) {
+            const int b = it & 1, q4 = it & 3;
             const long long n0 = tile * TN;
             const int nvalid = (int)min((long long)TN, p.N - n0);
             const int* srow = srow0 + q4 * 68;
-            const int ebase = srow[0];
             const float* lb = land0 + (size_t)b * cap * DP + 4 * lig;
-            const float* sv = sval0 + (size_t)q3 * cap;
+            const float* sv = sval0 + (size_t)q4 * cap;
             float* tb = tile0 + (size_t)b * TN * SA + DP + 4 * lig;
+            mbar_wait(&bar_landed[b], (it >> 1) & 1);                  // rows, row pointers (and weights) of tile it are in shared memory
+            if (it >= 2) named_bar_sync(GNN_BAR_EMPTY0 + b, WS_PAIR);  // MLP group b is done with tile it-2
+            const int ebase = srow[0];
+            // segment sums of this lane group's NPG nodes out of the landing zone, stored order
 #pragma unroll 1
             for (int u = 0; u < NPG; ++u) {
                 const int i = grp * NPG + u;
@@ -214,47 +252,13 @@ __global__ void __launch_bounds__(WS_THREADS, 1) state_iter_ws_kernel(const Iter
                     const float sc = sscale0[q4 * TN + i];
                     acc.x *= sc; acc.y *= sc; acc.z *= sc; acc.w *= sc;
                 }
-                if (p.agg_save && i < nvalid) st4_hint(p.agg_save + (size_t)(n0 + i) * DP + 4 * lig, acc, l2_policy_evict_first());
+                if (p.agg_save && i < nvalid) st4_hint(p.agg_save + (size_t)(n0 + i) * DP + 4 * lig, acc, stream_pol);
                 st4(tb + i * SA, acc);
             }
-        };
-
-        // Pipeline (the gather warps run one tile ahead of the MLP warps; nothing they wait for is on the critical path):
-        //   iteration it : rows(it+1) -> landing[b^1] and row pointers(it+3) -> srow        [asynchronous, group X_it]
-        //                  wait X_{it-1}: rows(it) and row pointers(it+2) have landed
-        //                  arc sources(it+2) -> registers (latency overlaps consume)
-        //                  wait EMPTY[b] (MLP group b finished tile it-2, long ago) ; consume(it) -> tile[b] ; FULL[b]
-        //                  arc sources(it+2) -> scol
-        // (own state rows and constant rows are fetched by the MLP group that owns the tile buffer)
-        auto tile_at = [&](int seq) { return first + (long long)seq * stride; };
-        for (int sq = 0; sq < 3; ++sq)
-            if (tile_at(sq) < ntiles) stage_rowptr_async(tile_at(sq), sq);
-        cp_async_commit();
-        cp_async_wait_group<0>();
-        named_bar_sync(GNN_BAR_GATHER, WS_GATHER);
-        for (int sq = 0; sq < 2; ++sq)
-            if (tile_at(sq) < ntiles) { load_cols(sq); store_cols(sq, sq); }
-        named_bar_sync(GNN_BAR_GATHER, WS_GATHER);
-        if (first < ntiles) issue_rows(0, 0, 0);
-        cp_async_commit();   // plays the role of X_{-1}
-        int it = 0;
-        for (long long tile = first; tile < ntiles; tile += stride, ++it) {
-            const int b = it & 1;
-            const long long t1 = tile + stride, t2 = tile + 2 * stride, t3 = tile + 3 * stride;
-            named_bar_sync(GNN_BAR_GATHER, WS_GATHER);     // consume(it-1) and store_cols(it+1) are done in every gather thread
-            if (t1 < ntiles) issue_rows((it + 1) & 3, (it + 1) % 3, b ^ 1);
-            if (t3 < ntiles) stage_rowptr_async(t3, (it + 3) & 3);
-            cp_async_commit();                             // X_it
-            cp_async_wait_group<1>();                      // everything older than X_it has landed
-            named_bar_sync(GNN_BAR_GATHER, WS_GATHER);     // ... for every gather thread
-            if (t2 < ntiles) load_cols((it + 2) & 3);
-            if (it >= 2) named_bar_sync(GNN_BAR_EMPTY0 + b, WS_PAIR);   // MLP group b is done with tile it-2
-            consume(tile, it & 3, it % 3, b);
+            mbar_arrive(&bar_free[b]);
             __threadfence_block();
             named_bar_arrive(GNN_BAR_FULL0 + b, WS_PAIR);
-            if (t2 < ntiles) store_cols((it + 2) & 3, (it + 2) % 3);
         }
-        cp_async_wait_group<0>();
     } else {
         // ============================================= MLP WARPS ==============================================
         // two MLP groups of 4 warps: group g takes the tiles with sequence number it = g, g+2, ... (= tile buffer g).
