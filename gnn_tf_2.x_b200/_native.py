@@ -42,7 +42,7 @@ class gnn_mlp_grad(C.Structure):
 class gnn_graph(C.Structure):
     _fields_ = [('n_nodes', C.c_int64), ('n_arcs', C.c_int64),
                 ('rowptr', C.c_void_p), ('col', C.c_void_p), ('val', C.c_void_p), ('row_scale', C.c_void_p),
-                ('rowptr_T', C.c_void_p), ('col_T', C.c_void_p), ('val_T', C.c_void_p)]
+                ('rowptr_T', C.c_void_p), ('col_T', C.c_void_p), ('val_T', C.c_void_p), ('max_block16_arcs', C.c_int32)]
 
 
 class gnn_loop_args(C.Structure):
@@ -205,6 +205,7 @@ def make_graph(adj) -> gnn_graph:
     else:
         g.val, g.row_scale, g.val_T = _ptr(adj.values), None, _ptr(adj.values_T)
     g.rowptr_T, g.col_T = _ptr(adj.rowptr_T), _ptr(adj.col_T)
+    g.max_block16_arcs = adj.max_block16_arcs
     return g
 
 

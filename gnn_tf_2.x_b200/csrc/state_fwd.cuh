@@ -46,6 +46,7 @@ struct IterParams {
     uint32_t seed;
     int training;
     int scol_cap;
+    int ring_slots, slot_rows;   // warp-specialised kernel: landing ring = ring_slots x slot_rows state rows
     NetLayout net;
 };
 

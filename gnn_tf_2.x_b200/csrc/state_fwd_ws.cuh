@@ -4,18 +4,24 @@
 // microbenchmark on B200 (scripts/gather_microbench.cu) needs >= 1000 rows in flight per SM to reach the L2/HBM limit;
 // the symmetric kernel (state_fwd.cuh) holds its rows in registers and cannot have that many in flight next to the MLP.
 // Here the rows land in shared memory through cp.async (no registers, deep queue) and THREE roles run concurrently in
-// one persistent CTA of 512 threads per SM (64-node tiles, double-buffered tiles and landing zones):
+// one persistent CTA of 512 threads per SM.  Work unit of the gather: a SUB-TILE of 16 nodes (= one m16 mma block);
+// 4 sub-tiles = one 64-node tile.  The landing zone is ONE ring of rows; every sub-tile owns a contiguous range of it
+// from the moment its copies are issued until its segment sums are done, so almost all of the ring is in flight at any
+// time (a ring of two whole-tile stages spends half of its life waiting to be consumed).
 //
 //   issue warps   (4): never wait for data.  Per tile: arc sources / row pointers of tile j+2 -> shared memory
-//                      (cp.async, completion -> mbarrier COLS), then one 16-byte cp.async per lane for every source row
-//                      of tile j -> landing[j&1]; completion of all of them arrives on mbarrier LANDED[j&1]
-//                      (cp.async.mbarrier.arrive.noinc).  They block only on the LSU queue, i.e. the memory pipe is fed
-//                      continuously -- the issue loop alone runs at the gather floor of the microbenchmark.
-//   consume warps (4): wait LANDED[j&1] -> segment sums out of shared memory in stored order (deterministic, no
-//                      atomics) into tile[j&1]  -> FULL[j&1] for the MLP, mbarrier FREE[j&1] for the issue warps
-//   MLP warps     (8): two groups of 4, even / odd tiles.  wait FULL -> Dense layer on the tensor cores (mma.sync
-//                      m16n8k8, 3xTF32 = fp32-accurate) -> bias / activation / affine -> store of the new state +
-//                      convergence test (+ BatchNormalization batch statistics when training)          -> EMPTY[j&1]
+//                      (cp.async, completion -> mbarrier COLS); per sub-tile: allocate ring rows (waiting for the oldest
+//                      sub-tiles to be released when the ring is full), one 16-byte cp.async per lane for every source
+//                      row; completion of all of them arrives on the sub-tile's mbarrier LANDED
+//                      (cp.async.mbarrier.arrive.noinc).  They block only on the LSU queue: the memory pipe is fed
+//                      continuously.
+//   consume warps (4): warp c owns sub-tile c of every tile.  wait LANDED -> segment sums out of shared memory in stored
+//                      order (deterministic, no atomics) into rows 16c..16c+15 of tile[j&1] -> mbarrier FULL[j&1][c] for
+//                      MLP warp c of group j&1, mbarrier FREE for the issue warps
+//   MLP warps     (8): two groups of 4, even / odd tiles; warp c owns rows 16c..16c+15: own state / constant rows by
+//                      cp.async, wait FULL -> Dense layer on the tensor cores (mma.sync m16n8k8, 3xTF32 = fp32-accurate)
+//                      -> bias / activation / affine -> store of the new state + convergence test (+ BatchNormalization
+//                      batch statistics when training) -> mbarrier EMPTY[j&1][c].  No block-wide barrier in the loop.
 //
 // Used for single-Dense-layer state nets (what the reference builds by default) with padded state width 16..32 and no
 // active dropout; every other case runs the symmetric kernel.
@@ -53,12 +59,18 @@ __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) 
 }
 
 constexpr int WS_TN = 64;          // nodes per tile
+constexpr int WS_SUB = 16;         // nodes per sub-tile (one m16 block, one consume warp, one MLP warp)
+constexpr int WS_NSUB = WS_TN / WS_SUB;
 constexpr int WS_MLP = 128;        // threads of ONE MLP group (4 warps); two groups: even / odd tiles
 constexpr int WS_MLP_ALL = 256;    // both MLP groups (warps 0-7)
 constexpr int WS_CONS = 128;       // consume threads (warps 8-11)
-constexpr int WS_ISSUE = 128;      // issue threads (warps 12-15)
-constexpr int WS_THREADS = 512;
-constexpr int WS_PAIR = WS_MLP + WS_CONS;     // participants of a FULL / EMPTY barrier: one MLP group + the consume warps
+constexpr int WS_ISSUE = 256;      // issue threads (warps 12-19): two groups of 4 warps, even / odd sub-tiles
+constexpr int WS_ISSUE_GRP = 128;
+constexpr int WS_THREADS = 640;
+// registers per thread after the roles split (setmaxnreg): 640 x 96 at launch -> MLP 128, consume 72, issue 56
+constexpr int WS_REGS_MLP = 128, WS_REGS_CONS = 72, WS_REGS_ISSUE = 56;
+constexpr int WS_SLOTS = 16;       // sub-tiles in flight at most (mbarrier slots of the ring)
+constexpr int WS_ROWQ = 8;         // row-pointer / scale buffers (tiles)
 
 // mbarrier (shared memory, CTA scope)
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
@@ -83,26 +95,28 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // weights in shared memory: the Dense kernel in mma B-fragment order (K padded to a multiple of 8), bias, affine a / c
 static inline size_t ws_weight_floats(const NetLayout& lay) { return (size_t)((lay.KP + 7) / 8) * 8 * lay.DP + 3 * (size_t)lay.DP; }
 
-// shared-memory footprint (bytes) for a landing capacity of `cap` rows per stage
-static inline size_t ws_smem_bytes(const NetLayout& lay, int cap, bool has_val) {
-    size_t fl = ws_weight_floats(lay) + 2 * (size_t)WS_TN * lay.SA + 2 * (size_t)cap * lay.DP + 4 * 68 + 4 * WS_TN +
-                3 * (size_t)cap + (has_val ? 4 * (size_t)cap : 0);   // tiles x2, landing x2, row pointers / scales x4, arc indices x3, weights x4
+// shared-memory footprint (bytes): `ring` landing rows (slots x rows per slot), arc-index capacity `capc` per tile
+static inline size_t ws_smem_bytes(const NetLayout& lay, int ring, int capc, bool has_val) {
+    size_t fl = ws_weight_floats(lay) + 2 * (size_t)WS_TN * lay.SA + (size_t)ring * lay.DP + WS_ROWQ * 68 + WS_ROWQ * WS_TN +
+                3 * (size_t)capc + (has_val ? WS_ROWQ * (size_t)capc : 0);   // tiles x2, ring, row pointers / scales, arc indices x3, weights
     return fl * 4;
 }
 
 template <int DP, bool HAS_VAL>
 __global__ void __launch_bounds__(WS_THREADS, 1) state_iter_ws_kernel(const IterParams p) {
     constexpr int TN = WS_TN, LPN = DP / 4;
-    constexpr int NGRP = WS_CONS / LPN;   // lane groups among the consume (and among the issue) warps
-    constexpr int NPG = TN / NGRP;        // consecutive nodes per consume lane group
-    static_assert(NPG >= 1 && NGRP * NPG == TN && WS_CONS == WS_ISSUE, "lane mapping");
-    static_assert(DP % 8 == 0 && TN == 64, "4 MLP warps x 16 nodes, DP / 8 accumulator fragments each");
+    constexpr int GPW = 32 / LPN;            // lane groups per warp
+    constexpr int NGRP = WS_ISSUE_GRP / LPN; // lane groups of one issue group
+    constexpr int NPG = WS_SUB / GPW;        // nodes per lane group of a consume warp
+    static_assert(GPW * NPG == WS_SUB, "lane mapping");
+    static_assert(DP % 8 == 0 && TN == 64 && WS_NSUB == 4, "4 MLP warps x 16 nodes, DP / 8 accumulator fragments each");
 
     if (*reinterpret_cast<const volatile int*>(p.go_cur) == 0) return;
 
     const NetLayout& net = p.net;
     const int tid = threadIdx.x;
-    const int SA = net.SA, CP = net.CP, KP = net.KP, cap = p.scol_cap;
+    const int SA = net.SA, CP = net.CP, KP = net.KP, capc = p.scol_cap;
+    const int nslot = p.ring_slots, slotcap = p.slot_rows;   // landing ring: nslot slots of slotcap rows, sub-tile j -> slot j % nslot
 
     extern __shared__ __align__(16) float smem[];
     constexpr int NT8 = DP / 8;
@@ -111,13 +125,13 @@ __global__ void __launch_bounds__(WS_THREADS, 1) state_iter_ws_kernel(const Iter
     float* sBias = sW + KS * 8 * DP;                    // [DP]
     float* sAff = sBias + DP;                           // a[DP], c[DP]
     float* tile0 = sAff + 2 * DP;                       // [2][TN][SA]
-    float* land0 = tile0 + 2 * TN * SA;                 // [2][cap][DP]
-    int* srow0 = reinterpret_cast<int*>(land0 + 2 * (size_t)cap * DP);   // [4][68]
-    float* sscale0 = reinterpret_cast<float*>(srow0 + 4 * 68);           // [4][TN]
-    int* scol0 = reinterpret_cast<int*>(sscale0 + 4 * TN);               // [3][cap]
-    float* sval0 = reinterpret_cast<float*>(scol0 + 3 * cap);            // [4][cap] (HAS_VAL; read by the consume warps)
+    float* land0 = tile0 + 2 * TN * SA;                 // [nslot][slotcap][DP]
+    int* srow0 = reinterpret_cast<int*>(land0 + (size_t)nslot * slotcap * DP);   // [WS_ROWQ][68]
+    float* sscale0 = reinterpret_cast<float*>(srow0 + WS_ROWQ * 68);     // [WS_ROWQ][TN]
+    int* scol0 = reinterpret_cast<int*>(sscale0 + WS_ROWQ * TN);         // [3][capc]
+    float* sval0 = reinterpret_cast<float*>(scol0 + 3 * capc);           // [WS_ROWQ][capc] (HAS_VAL; read by the consume warps)
     __shared__ int s_flag;
-    __shared__ __align__(8) uint64_t bar_landed[2], bar_free[2], bar_cols[3];
+    __shared__ __align__(8) uint64_t bar_landed[WS_SLOTS], bar_free[WS_SLOTS], bar_cols[3], bar_full[2][WS_NSUB], bar_empty[2][WS_NSUB];
 
     // the Dense kernel in mma B-fragment order:
     //   sW[((ks * NT8 + nt) * 32 + lane) * 2 + h] = W[8 ks + (lane & 3) + 4 h][8 nt + (lane >> 2)]   (0 beyond KP)
@@ -133,8 +147,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) state_iter_ws_kernel(const Iter
     }
     if (tid == 0) {
         s_flag = 0;
-        for (int i = 0; i < 2; ++i) { mbar_init(&bar_landed[i], WS_ISSUE); mbar_init(&bar_free[i], WS_CONS); }
+        for (int i = 0; i < WS_SLOTS; ++i) { mbar_init(&bar_landed[i], WS_ISSUE_GRP); mbar_init(&bar_free[i], 32); }
         for (int i = 0; i < 3; ++i) mbar_init(&bar_cols[i], WS_ISSUE);
+        for (int i = 0; i < 2 * WS_NSUB; ++i) { mbar_init(&bar_full[0][0] + i, 32); mbar_init(&bar_empty[0][0] + i, 32); }
     }
     __syncthreads();
 
@@ -142,50 +157,49 @@ __global__ void __launch_bounds__(WS_THREADS, 1) state_iter_ws_kernel(const Iter
     const long long first = blockIdx.x, stride = gridDim.x;
     auto tile_at = [&](int seq) { return first + (long long)seq * stride; };
 
+    // sub-tile c of a tile lands the arcs [a0, a0 + cnt) (tile-relative) in its ring slot; arcs beyond the slot (or beyond
+    // the staged arc indices) are read directly by the consume warp
+    auto sub_range = [&](const int* srow, int c, int& a0, int& cnt) {
+        const int ebase = srow[0];
+        a0 = srow[WS_SUB * c] - ebase;
+        const int a1 = min(srow[WS_SUB * c + WS_SUB] - ebase, capc);
+        cnt = max(0, min(a1 - a0, slotcap));
+    };
+
     if (tid >= WS_MLP_ALL + WS_CONS) {
         // ============================================ ISSUE WARPS ==============================================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(WS_REGS_ISSUE));
         const int gt = tid - WS_MLP_ALL - WS_CONS;
-        const int grp = gt / LPN, lig = gt % LPN;
-        const uint64_t keep = l2_policy_evict_last();
+        const int ig = gt / WS_ISSUE_GRP;                       // issue group: sub-tiles ig, ig + 2 of every tile
+        const int grp = (gt % WS_ISSUE_GRP) / LPN, lig = gt % LPN;
 
-        // Buffers: landing zones x2 (b = seq & 1), arc indices x3 (seq % 3), row pointers / scales x4 (seq & 3).
         // arc sources (+ weights), row pointers (+ per-node scales) of tile seq: asynchronous 4-byte copies.  The arc range
         // [e0, e1) comes from registers (read one iteration earlier straight from global memory).
         auto request_cols = [&](long long tile, int seq, int e0, int e1) {
             const long long n0 = tile * TN;
-            const int q4 = seq & 3, q3 = seq % 3;
-            const int ecount = min(e1 - e0, cap);
+            const int q8 = seq & (WS_ROWQ - 1), q3 = seq % 3;
+            const int ecount = min(e1 - e0, capc);
             for (int r = gt; r < ecount; r += WS_ISSUE) {
-                cp_async4(scol0 + (size_t)q3 * cap + r, p.col + e0 + r);
-                if (HAS_VAL) cp_async4(sval0 + (size_t)q4 * cap + r, p.val + e0 + r);
+                cp_async4(scol0 + (size_t)q3 * capc + r, p.col + e0 + r);
+                if (HAS_VAL) cp_async4(sval0 + (size_t)q8 * capc + r, p.val + e0 + r);
             }
-            for (int i = gt; i <= TN; i += WS_ISSUE) cp_async4(srow0 + q4 * 68 + i, p.rowptr + min(n0 + i, p.N));
+            for (int i = gt; i <= TN; i += WS_ISSUE) cp_async4(srow0 + q8 * 68 + i, p.rowptr + min(n0 + i, p.N));
             if (!HAS_VAL)
                 for (int i = gt; i < TN; i += WS_ISSUE) {
-                    if (n0 + i < p.N) cp_async4(sscale0 + q4 * TN + i, p.cst + (size_t)(n0 + i) * CP + net.C);
-                    else sscale0[q4 * TN + i] = 0.f;
+                    if (n0 + i < p.N) cp_async4(sscale0 + q8 * TN + i, p.cst + (size_t)(n0 + i) * CP + net.C);
+                    else sscale0[q8 * TN + i] = 0.f;
                 }
         };
         auto tile_arcs = [&](long long tile, int& e0, int& e1) {
             e0 = __ldg(p.rowptr + tile * TN);
             e1 = __ldg(p.rowptr + min(tile * TN + TN, p.N));
         };
-        // every source row of the tile -> landing zone b (asynchronous, no registers); a lane group takes chunks of 4
-        // consecutive arcs so that their 4 indices are one 128-bit shared-memory load
-        auto issue_rows = [&](int seq) {
-            const int* srow = srow0 + (seq & 3) * 68;
-            const int ecount = min(srow[TN] - srow[0], cap);
-            float* lb = land0 + (size_t)(seq & 1) * cap * DP + 4 * lig;
-            const int* scol = scol0 + (size_t)(seq % 3) * cap;
-            const float* xl = p.x_in + 4 * lig;
-            for (int r = 4 * grp; r < ecount; r += 4 * NGRP) {
-                const int4 s4 = *reinterpret_cast<const int4*>(scol + r);   // entries past ecount are never used
-                cp_async16_hint(lb + (size_t)r * DP, xl + (size_t)s4.x * DP, keep);
-                if (r + 1 < ecount) cp_async16_hint(lb + (size_t)(r + 1) * DP, xl + (size_t)s4.y * DP, keep);
-                if (r + 2 < ecount) cp_async16_hint(lb + (size_t)(r + 2) * DP, xl + (size_t)s4.z * DP, keep);
-                if (r + 3 < ecount) cp_async16_hint(lb + (size_t)(r + 3) * DP, xl + (size_t)s4.w * DP, keep);
-            }
-        };
+
+        // nslot is even: slot j % nslot has the parity of the sub-tile, i.e. a slot is only ever used by ONE issue group,
+        // which is therefore the only thread set waiting on its FREE barrier (never more than one phase behind)
+        int slot = ig, m = 0;                   // slot (= j % nslot) of this group's next sub-tile; sub-tiles issued so far
+        int wphase = 0;                         // FREE phase to wait for; flips each time `slot` wraps
+        const int per_round = nslot / 2;        // this group's slots
 
         int e0, e1;
         for (int sq = 0; sq < 2; ++sq)
@@ -197,76 +211,112 @@ __global__ void __launch_bounds__(WS_THREADS, 1) state_iter_ws_kernel(const Iter
         if (tile_at(2) < ntiles) tile_arcs(tile_at(2), e0, e1);     // arc range of tile it + 2, one iteration ahead
         int it = 0;
         for (long long tile = first; tile < ntiles; tile += stride, ++it) {
-            const int b = it & 1;
             const long long t2 = tile + 2 * stride, t3 = tile + 3 * stride;
+            // Buffers request_cols is about to overwrite hold the row pointers / scales / weights of tile it+2-WS_ROWQ = it-6.
+            // A sub-tile x of that tile shares its slot with y = x + nslot, a sub-tile of a tile <= it-2 (nslot <= 16);
+            // y has been issued (everybody is past tile it-1), and y is only issued after x has been consumed.
             named_bar_sync(GNN_BAR_ISSUE, WS_ISSUE);                 // every issue thread is done reading the indices of tile it-1
-            if (it >= 2) mbar_wait(&bar_free[b], ((it >> 1) - 1) & 1);   // tile it-2 is consumed: landing[b], srow[(it+2)&3] are free
             if (t2 < ntiles) {
                 request_cols(t2, it + 2, e0, e1);
                 cp_async_mbar_arrive(&bar_cols[(it + 2) % 3]);
             }
             if (t3 < ntiles) tile_arcs(t3, e0, e1);
             mbar_wait(&bar_cols[it % 3], (it / 3) & 1);              // indices / row pointers of tile it have landed
-            issue_rows(it);
-            cp_async_mbar_arrive(&bar_landed[b]);
+            const int* srow = srow0 + (it & (WS_ROWQ - 1)) * 68;
+            const int* scol = scol0 + (size_t)(it % 3) * capc;
+            const float* xl = p.x_in + 4 * lig;
+#pragma unroll 1
+            for (int c = ig; c < WS_NSUB; c += 2) {
+                int a0, cnt;
+                sub_range(srow, c, a0, cnt);
+                if (m >= per_round) mbar_wait(&bar_free[slot], wphase);   // the slot's previous sub-tile has been consumed
+                const int start = slot * slotcap;
+                // every landed source row -> ring (asynchronous, no registers): one row per lane group and step
+                float* lb = land0 + (size_t)start * DP + 4 * lig;
+                const int* sc = scol + a0;
+                int r = grp;
+                for (; r < cnt - 3 * NGRP; r += 4 * NGRP) {          // 4 independent index loads, then 4 copies
+                    const int s0 = sc[r], s1 = sc[r + NGRP], s2 = sc[r + 2 * NGRP], s3 = sc[r + 3 * NGRP];
+                    cp_async16(lb + (size_t)r * DP, xl + (size_t)s0 * DP);
+                    cp_async16(lb + (size_t)(r + NGRP) * DP, xl + (size_t)s1 * DP);
+                    cp_async16(lb + (size_t)(r + 2 * NGRP) * DP, xl + (size_t)s2 * DP);
+                    cp_async16(lb + (size_t)(r + 3 * NGRP) * DP, xl + (size_t)s3 * DP);
+                }
+                if (r < cnt - NGRP) {
+                    const int s0 = sc[r], s1 = sc[r + NGRP];
+                    cp_async16(lb + (size_t)r * DP, xl + (size_t)s0 * DP);
+                    cp_async16(lb + (size_t)(r + NGRP) * DP, xl + (size_t)s1 * DP);
+                    r += 2 * NGRP;
+                }
+                if (r < cnt) cp_async16(lb + (size_t)r * DP, xl + (size_t)sc[r] * DP);
+                cp_async_mbar_arrive(&bar_landed[slot]);
+                slot += 2;
+                ++m;
+                if (slot >= nslot) { slot -= nslot; if (m > per_round) wphase ^= 1; }
+            }
         }
         cp_async_wait_group<0>();
     } else if (tid >= WS_MLP_ALL) {
         // =========================================== CONSUME WARPS =============================================
-        const int gt = tid - WS_MLP_ALL;
-        const int grp = gt / LPN, lig = gt % LPN;
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(WS_REGS_CONS));
+        const int cw = (tid - WS_MLP_ALL) >> 5;             // this warp's sub-tile of every tile
+        const int lane = tid & 31, grpw = lane / LPN, lig = lane % LPN;
         const uint64_t stream_pol = l2_policy_evict_first();
-        int it = 0;
+        int it = 0, slot = cw, phase = 0;                   // slot / mbarrier phase of sub-tile j = 4 it + cw (nslot >= 4)
         for (long long tile = first; tile < ntiles; tile += stride, ++it) {
-            const int b = it & 1, q4 = it & 3;
+            const int b = it & 1, q8 = it & (WS_ROWQ - 1);
             const long long n0 = tile * TN;
             const int nvalid = (int)min((long long)TN, p.N - n0);
-            const int* srow = srow0 + q4 * 68;
-            const float* lb = land0 + (size_t)b * cap * DP + 4 * lig;
-            const float* sv = sval0 + (size_t)q4 * cap;
-            float* tb = tile0 + (size_t)b * TN * SA + DP + 4 * lig;
-            mbar_wait(&bar_landed[b], (it >> 1) & 1);                  // rows, row pointers (and weights) of tile it are in shared memory
-            if (it >= 2) named_bar_sync(GNN_BAR_EMPTY0 + b, WS_PAIR);  // MLP group b is done with tile it-2
+            const int* srow = srow0 + q8 * 68;
+            mbar_wait(&bar_landed[slot], phase);            // rows of the sub-tile, row pointers (and weights) of the tile
+            int a0, cnt;
+            sub_range(srow, cw, a0, cnt);
+            const int start = slot * slotcap;
+            if (it >= 2) mbar_wait(&bar_empty[b][cw], ((it >> 1) - 1) & 1);   // MLP warp cw of group b is done with tile it-2
             const int ebase = srow[0];
-            // segment sums of this lane group's NPG nodes out of the landing zone, stored order
+            const float* lb = land0 + ((size_t)start - a0) * DP + 4 * lig;   // row of tile-relative arc r: lb + r * DP
+            const float* sv = sval0 + (size_t)q8 * capc;
+            float* tb = tile0 + (size_t)b * TN * SA + DP + 4 * lig;
+            // segment sums of this lane group's NPG nodes out of the ring, stored order
 #pragma unroll 1
             for (int u = 0; u < NPG; ++u) {
-                const int i = grp * NPG + u;
+                const int i = WS_SUB * cw + grpw * NPG + u;
                 const int r0 = srow[i] - ebase, r1 = srow[i + 1] - ebase;
                 float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
                 int r = r0;
-                const int rl = min(r1, cap);
+                const int rl = min(r1, a0 + cnt);
 #pragma unroll 4
                 for (; r < rl; ++r) {
-                    const float4 v = ld4(lb + (size_t)r * DP);
+                    const float4 v = ld4(lb + (ptrdiff_t)r * DP);
                     if (HAS_VAL) acc = fma4(sv[r], v, acc);
                     else acc = add4(acc, v);
                 }
-                for (; r < r1; ++r) {   // arcs beyond the landing capacity: direct loads (rare, high-degree tiles)
+                for (; r < r1; ++r) {   // arcs that did not get ring rows: direct loads (rare, very dense sub-tiles)
                     const int s = __ldg(p.col + ebase + r);
                     const float4 v = ldg4(p.x_in + (size_t)s * DP + 4 * lig);
                     if (HAS_VAL) acc = fma4(__ldg(p.val + ebase + r), v, acc);
                     else acc = add4(acc, v);
                 }
                 if (!HAS_VAL) {
-                    const float sc = sscale0[q4 * TN + i];
+                    const float sc = sscale0[q8 * TN + i];
                     acc.x *= sc; acc.y *= sc; acc.z *= sc; acc.w *= sc;
                 }
                 if (p.agg_save && i < nvalid) st4_hint(p.agg_save + (size_t)(n0 + i) * DP + 4 * lig, acc, stream_pol);
                 st4(tb + i * SA, acc);
             }
-            mbar_arrive(&bar_free[b]);
-            __threadfence_block();
-            named_bar_arrive(GNN_BAR_FULL0 + b, WS_PAIR);
+            mbar_arrive(&bar_free[slot]);
+            mbar_arrive(&bar_full[b][cw]);
+            slot += WS_NSUB;
+            if (slot >= nslot) { slot -= nslot; phase ^= 1; }
         }
     } else {
         // ============================================= MLP WARPS ==============================================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(WS_REGS_MLP));
         // two MLP groups of 4 warps: group g takes the tiles with sequence number it = g, g+2, ... (= tile buffer g).
-        // Inside a group warp w owns nodes [16 w, 16 w + 16) of the tile and all DP outputs: NT8 accumulator fragments
-        constexpr int CG = DP / 4;
+        // Inside a group warp w owns nodes [16 w, 16 w + 16) of the tile and all DP outputs: NT8 accumulator fragments.
+        // The warps are independent of each other: each one pairs with consume warp w through FULL / EMPTY[g][w].
         const int mgroup = tid / WS_MLP, mt = tid % WS_MLP;
         const int mwarp = mt >> 5, lane = mt & 31, fg = lane >> 2, ft = lane & 3;   // fragment coordinates (groupID, thread-in-group)
-        const int lig = mt % LPN;
         const float* bias = sBias;
         const float* aff_a = sAff;
         const float* aff_c = sAff + DP;
@@ -277,20 +327,22 @@ __global__ void __launch_bounds__(WS_THREADS, 1) state_iter_ws_kernel(const Iter
 #pragma unroll
         for (int c = 0; c < 2 * NT8; ++c) bn_s1[c] = bn_s2[c] = 0.;
         bool any_moving = false;
-        // own state rows and constant rows of a tile -> this group's tile buffer (asynchronous; the gather warps only
-        // write the aggregate columns, so the two never touch the same bytes)
+        // own state rows and constant rows of this warp's 16 nodes -> tile buffer (asynchronous; the consume warp only
+        // writes the aggregate columns, so the two never touch the same bytes)
         float* tb = tile0 + (size_t)mgroup * TN * SA;
+        const int cpq = CP / 4;
         auto issue_own = [&](long long tile) {
             const long long n0 = tile * TN;
             const int nvalid = (int)min((long long)TN, p.N - n0);
-            for (int item = mt; item < TN * LPN; item += WS_MLP) {
-                const int i = item / LPN;
-                float* dstp = tb + i * SA + 4 * lig;
-                if (i < nvalid) cp_async16(dstp, p.x_in + (size_t)(p.row_offset + n0 + i) * DP + 4 * lig);
+#pragma unroll
+            for (int item = lane; item < WS_SUB * LPN; item += 32) {
+                const int i = WS_SUB * mwarp + item / LPN, l = item % LPN;
+                float* dstp = tb + i * SA + 4 * l;
+                if (i < nvalid) cp_async16(dstp, p.x_in + (size_t)(p.row_offset + n0 + i) * DP + 4 * l);
                 else st4(dstp, make_float4(0.f, 0.f, 0.f, 0.f));
             }
-            for (int item = mt; item < TN * (CP / 4); item += WS_MLP) {
-                const int i = item / (CP / 4), c = item % (CP / 4);
+            for (int item = lane; item < WS_SUB * cpq; item += 32) {
+                const int i = WS_SUB * mwarp + item / cpq, c = item % cpq;
                 float* dstp = tb + i * SA + 2 * DP + 4 * c;
                 if (i < nvalid) cp_async16(dstp, p.cst + (size_t)(n0 + i) * CP + 4 * c);
                 else st4(dstp, make_float4(0.f, 0.f, 0.f, 0.f));
@@ -301,12 +353,11 @@ __global__ void __launch_bounds__(WS_THREADS, 1) state_iter_ws_kernel(const Iter
 
         int it = mgroup;
         for (long long tile = first + (long long)mgroup * stride; tile < ntiles; tile += 2 * stride, it += 2) {
-            const int b = mgroup;
             const long long n0 = tile * TN;
             const int nvalid = (int)min((long long)TN, p.N - n0);
-            named_bar_sync(GNN_BAR_FULL0 + b, WS_PAIR);            // aggregates of this tile are in the buffer
-            cp_async_wait_group<0>();                              // my own / constant rows too ...
-            named_bar_sync(GNN_BAR_MLP0 + mgroup, WS_MLP);         // ... and those of the rest of the group
+            mbar_wait(&bar_full[mgroup][mwarp], (it >> 1) & 1);    // aggregates of my 16 nodes are in the buffer
+            cp_async_wait_group<0>();                              // my part of the own / constant rows too ...
+            __syncwarp();                                          // ... and those of the other lanes
 
             // Dense layer on the tensor cores: 16 x DP outputs per warp, K in steps of 8, 3 x TF32 (fp32-accurate)
             float acc[NT8][4];
@@ -429,11 +480,10 @@ __global__ void __launch_bounds__(WS_THREADS, 1) state_iter_ws_kernel(const Iter
                 case GNN_ACT_SOFTPLUS: epilogue(std::integral_constant<int, GNN_ACT_SOFTPLUS>{}); break;
                 default: epilogue(std::integral_constant<int, GNN_ACT_LINEAR>{}); break;
             }
-            if (tile + 2 * stride < ntiles) {   // this buffer's next tile: fetch its own rows, then hand the buffer back
-                named_bar_sync(GNN_BAR_MLP0 + mgroup, WS_MLP);   // the whole group has finished reading the tile
+            if (tile + 2 * stride < ntiles) {   // this buffer's next tile: fetch its own rows, then hand the rows back
+                __syncwarp();                   // every lane has finished reading the old rows
                 issue_own(tile + 2 * stride);
-                __threadfence_block();
-                named_bar_arrive(GNN_BAR_EMPTY0 + b, WS_PAIR);
+                mbar_arrive(&bar_empty[mgroup][mwarp]);
             }
         }
 

@@ -174,6 +174,7 @@ struct Plan {
     IterKernel kernel;
     size_t smem;
     int scol_cap;
+    int ring_slots, slot_rows;
     int grid;
     bool has_val;
 };
@@ -199,18 +200,34 @@ int make_plan(const gnn_graph* g, const gnn_mlp* net, const gnn_loop_args* a, Pl
     const KernelSet* ks = kernel_set(lay.DP);
     if (!ks) GNN_FAIL(GNN_ERR_UNSUPPORTED, "no kernel for padded state width %d", lay.DP);
     plan->ws = false;
+    plan->ring_slots = plan->slot_rows = 0;
 
     if (ws_applicable(g, a, lay, di.sms) && ks->iter_ws[plan->has_val ? 1 : 0]) {
-        // landing capacity: the average tile + 25 %, bounded by what one CTA per SM can hold
+        // arc-index capacity per tile: 1.5x the average tile; the landing ring takes all the shared memory that is left
+        // (at least 4 average sub-tiles, at most 4096 rows)
         const long long avg = g->n_nodes > 0 ? (g->n_arcs * WS_TN) / g->n_nodes : 0;
-        int cap = (int)std::min<long long>(4096, std::max<long long>(64, (avg * 5 / 4 + 15) / 16 * 16));
-        while (cap > 16 && ws_smem_bytes(lay, cap, plan->has_val) + 4608 > (size_t)di.smem_optin) cap -= 16;
-        if (ws_smem_bytes(lay, cap, plan->has_val) + 4608 <= (size_t)di.smem_optin) {
+        long long capc_want = avg * 3 / 2;
+        if (g->max_block16_arcs > 0) capc_want = std::min<long long>(capc_want, (long long)WS_NSUB * g->max_block16_arcs);   // no tile has more
+        const int capc = (int)std::min<long long>(4096, std::max<long long>(128, (capc_want + 15) / 16 * 16));
+        const size_t budget = (size_t)di.smem_optin - 5120;   // static shared memory of the kernel + slack
+        const size_t fixed = ws_smem_bytes(lay, 0, capc, plan->has_val);
+        const int ring = fixed < budget ? (int)std::min<size_t>(4096, (budget - fixed) / ((size_t)lay.DP * 4)) : 0;
+        // slots of the ring: one sub-tile (16 nodes) each.  When the caller knows the densest block of 16 rows the slot
+        // holds exactly that (bounded by 1.5x the average: hubs read their excess arcs directly); otherwise 1/8 above the
+        // average sub-tile.  As many slots as fit, at most WS_SLOTS.
+        const long long avg_sub = std::max<long long>(16, avg / WS_NSUB);
+        long long want = g->max_block16_arcs > 0 ? std::min<long long>(g->max_block16_arcs, std::max<long long>(32, avg_sub * 3 / 2))
+                                                 : avg_sub * 9 / 8;
+        const int slot_rows = (int)((want + 3) / 4 * 4);
+        const int slots = std::min(WS_SLOTS, ring / slot_rows) & ~1;   // even: a slot belongs to one issue group
+        if (slots >= 4) {
             plan->ws = true;
             plan->kernel = ks->iter_ws[plan->has_val ? 1 : 0];
             plan->ts = TileShape{WS_TN, WS_THREADS};
-            plan->scol_cap = cap;
-            plan->smem = ws_smem_bytes(lay, cap, plan->has_val);
+            plan->scol_cap = capc;
+            plan->ring_slots = slots;
+            plan->slot_rows = slot_rows;
+            plan->smem = ws_smem_bytes(lay, slots * slot_rows, capc, plan->has_val);
             int occ = 0;
             GNN_TRY(kernel_occupancy((const void*)plan->kernel, WS_THREADS, plan->smem, &occ));
             const long long ntiles = (g->n_nodes + WS_TN - 1) / WS_TN;
@@ -310,7 +327,7 @@ extern "C" int gnn_state_loop_forward(const gnn_graph* g, const gnn_mlp* net, co
     memset(&p, 0, sizeof(p));
     p.rowptr = g->rowptr; p.col = g->col; p.val = plan.has_val ? g->val : nullptr; p.N = N; p.row_offset = a->row_offset;
     p.cst = w.cst; p.wpack = w.wpack; p.k_ptr = kptr; p.thr = a->threshold; p.bn_partial = w.bn_partial;
-    p.bn_train = bn_train; p.seed = a->seed; p.training = a->training; p.scol_cap = plan.scol_cap; p.net = lay;
+    p.bn_train = bn_train; p.seed = a->seed; p.training = a->training; p.scol_cap = plan.scol_cap; p.ring_slots = plan.ring_slots; p.slot_rows = plan.slot_rows; p.net = lay;
     p.n_peers = a->n_global > 0 ? a->n_peers : 0; p.rank = a->rank; p.peer_mask = a->peer_mask;
     BnApplyKernel bn_apply = kernel_set(lay.DP)->bn_apply;
 

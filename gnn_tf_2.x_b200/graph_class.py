@@ -379,6 +379,20 @@ class SparseCSR:
     def nnz(self) -> int: return int(self.col.shape[0])
 
     @property
+    def max_block16_arcs(self) -> int:
+        """ largest number of stored entries in an aligned block of 16 rows (computed once, one device read): sizes the
+        landing-ring slots of the forward kernel (include/gnn_b200.h, gnn_graph.max_block16_arcs) """
+        if getattr(self, '_max_block16', None) is None:
+            import torch
+            n = int(self.rowptr.shape[0]) - 1
+            if n <= 0: self._max_block16 = 0
+            else:
+                idx = torch.arange(0, n + 16, 16, device=self.rowptr.device).clamp_(max=n)
+                b = self.rowptr[idx].to(torch.int64)
+                self._max_block16 = int((b[1:] - b[:-1]).max().item())
+        return self._max_block16
+
+    @property
     def indices(self):
         """ (nnz, 2) int64 [row, col] pairs in stored (row-major) order """
         import torch

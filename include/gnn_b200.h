@@ -117,6 +117,8 @@ typedef struct gnn_graph {
     const int32_t* rowptr_T;  /* [n_nodes+1] (backward only) */
     const int32_t* col_T;     /* [n_arcs] destination node, source-sorted */
     const float* val_T;       /* [n_arcs] weights in transposed order; NULL with row_scale */
+    int32_t max_block16_arcs; /* largest rowptr[16(b+1)] - rowptr[16b] over the aligned blocks of 16 rows (the last block may
+                                 be shorter); 0 = unknown.  Sizes the slots of the forward kernel's landing ring exactly */
 } gnn_graph;
 
 /* ------------------------------------------------------------------------------------------------------------
