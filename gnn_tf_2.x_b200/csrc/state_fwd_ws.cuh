@@ -67,8 +67,10 @@ constexpr int WS_CONS = 128;       // consume threads (warps 8-11)
 constexpr int WS_ISSUE = 256;      // issue threads (warps 12-19): two groups of 4 warps, even / odd sub-tiles
 constexpr int WS_ISSUE_GRP = 128;
 constexpr int WS_THREADS = 640;
-// registers per thread after the roles split (setmaxnreg): 640 x 96 at launch -> MLP 128, consume 72, issue 56
-constexpr int WS_REGS_MLP = 128, WS_REGS_CONS = 72, WS_REGS_ISSUE = 56;
+// registers per thread after the roles split (setmaxnreg): 640 x 96 at launch -> MLP 152, consume 64, issue 48
+constexpr int WS_REGS_MLP = 152, WS_REGS_CONS = 64, WS_REGS_ISSUE = 48;
+static_assert(8 * (WS_REGS_MLP - 96) <= 8 * (96 - WS_REGS_ISSUE) + 4 * (96 - WS_REGS_CONS),
+              "setmaxnreg.inc only draws on what this CTA's own warps released (spare registers of the SM do not count)");
 constexpr int WS_SLOTS = 16;       // sub-tiles in flight at most (mbarrier slots of the ring)
 constexpr int WS_ROWQ = 8;         // row-pointer / scale buffers (tiles)
 
@@ -92,12 +94,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     } while (!done);
 }
 
-// weights in shared memory: the Dense kernel in mma B-fragment order (K padded to a multiple of 8), bias, affine a / c
-static inline size_t ws_weight_floats(const NetLayout& lay) { return (size_t)((lay.KP + 7) / 8) * 8 * lay.DP + 3 * (size_t)lay.DP; }
+// aggregate tile row stride (floats): rows g and g+1 of a quarter-warp's 128-bit fragment loads fall in different bank halves
+static inline int ws_tile_stride(int DP) { return DP % 32 == 0 ? DP + 16 : DP; }
+// k-steps (8 inputs each) of the Dense layer: own state, constant row (padded to 8), aggregated state
+static inline int ws_ksteps(const NetLayout& lay) { return 2 * (lay.DP / 8) + (lay.CP + 7) / 8; }
+// weights in shared memory: B fragments {hi(b0), hi(b1), lo(b0), lo(b1)} per (k-step, n-tile, lane), bias, affine a / c
+static inline size_t ws_weight_floats(const NetLayout& lay) { return (size_t)ws_ksteps(lay) * (lay.DP / 8) * 128 + 3 * (size_t)lay.DP; }
 
 // shared-memory footprint (bytes): `ring` landing rows (slots x rows per slot), arc-index capacity `capc` per tile
 static inline size_t ws_smem_bytes(const NetLayout& lay, int ring, int capc, bool has_val) {
-    size_t fl = ws_weight_floats(lay) + 2 * (size_t)WS_TN * lay.SA + (size_t)ring * lay.DP + WS_ROWQ * 68 + WS_ROWQ * WS_TN +
+    size_t fl = ws_weight_floats(lay) + 2 * (size_t)WS_TN * ws_tile_stride(lay.DP) + (size_t)ring * lay.DP + WS_ROWQ * 68 + WS_ROWQ * WS_TN +
                 3 * (size_t)capc + (has_val ? WS_ROWQ * (size_t)capc : 0);   // tiles x2, ring, row pointers / scales, arc indices x3, weights
     return fl * 4;
 }
@@ -115,17 +121,19 @@ __global__ void __launch_bounds__(WS_THREADS, 1) state_iter_ws_kernel(const Iter
 
     const NetLayout& net = p.net;
     const int tid = threadIdx.x;
-    const int SA = net.SA, CP = net.CP, KP = net.KP, capc = p.scol_cap;
+    const int CP = net.CP, capc = p.scol_cap;
     const int nslot = p.ring_slots, slotcap = p.slot_rows;   // landing ring: nslot slots of slotcap rows, sub-tile j -> slot j % nslot
 
     extern __shared__ __align__(16) float smem[];
-    constexpr int NT8 = DP / 8;
-    const int KS = (KP + 7) / 8;
-    float* sW = smem;                                   // [KS][NT8][32 lanes][2]: B fragments of the Dense kernel
-    float* sBias = sW + KS * 8 * DP;                    // [DP]
+    constexpr int NT8 = DP / 8, NQ = DP / 16;           // n-tiles of 8 outputs; 16-column units of a state row
+    constexpr int SAG = DP % 32 == 0 ? DP + 16 : DP;    // aggregate tile row stride (ws_tile_stride)
+    const int CS = (CP + 7) / 8;                        // k-steps of the constant row
+    const int KSTEPS = 4 * NQ + CS;
+    float4* sW4 = reinterpret_cast<float4*>(smem);      // [KSTEPS][NT8][32 lanes]: B fragments {hi b0, hi b1, lo b0, lo b1}
+    float* sBias = smem + (size_t)KSTEPS * NT8 * 128;   // [DP]
     float* sAff = sBias + DP;                           // a[DP], c[DP]
-    float* tile0 = sAff + 2 * DP;                       // [2][TN][SA]
-    float* land0 = tile0 + 2 * TN * SA;                 // [nslot][slotcap][DP]
+    float* tile0 = sAff + 2 * DP;                       // [2][TN][SAG]: aggregated states
+    float* land0 = tile0 + 2 * TN * SAG;                // [nslot][slotcap][DP]
     int* srow0 = reinterpret_cast<int*>(land0 + (size_t)nslot * slotcap * DP);   // [WS_ROWQ][68]
     float* sscale0 = reinterpret_cast<float*>(srow0 + WS_ROWQ * 68);     // [WS_ROWQ][TN]
     int* scol0 = reinterpret_cast<int*>(sscale0 + WS_ROWQ * TN);         // [3][capc]
@@ -133,12 +141,30 @@ __global__ void __launch_bounds__(WS_THREADS, 1) state_iter_ws_kernel(const Iter
     __shared__ int s_flag;
     __shared__ __align__(8) uint64_t bar_landed[WS_SLOTS], bar_free[WS_SLOTS], bar_cols[3], bar_full[2][WS_NSUB], bar_empty[2][WS_NSUB];
 
-    // the Dense kernel in mma B-fragment order:
-    //   sW[((ks * NT8 + nt) * 32 + lane) * 2 + h] = W[8 ks + (lane & 3) + 4 h][8 nt + (lane >> 2)]   (0 beyond KP)
-    for (int i = tid; i < KS * NT8 * 64; i += WS_THREADS) {
-        const int h = i & 1, lane = (i >> 1) & 31, nt = (i >> 6) % NT8, ks = (i >> 6) / NT8;
-        const int k = 8 * ks + (lane & 3) + 4 * h, n = 8 * nt + (lane >> 2);
-        sW[i] = k < KP ? __ldg(p.wpack + net.w_off[0] + k * DP + n) : 0.f;
+    // The mma K and N indices are ours to permute as long as A, B and C agree.  Both are laid out so that a lane's fragment
+    // elements are CONTIGUOUS in memory (128-bit loads / stores, whole 32-byte sectors per 4 lanes):
+    //   K: k-steps 2q, 2q+1 of a 16-column unit q of a state row: lane ft holds columns 16q + 4ft + {0,1} (step 2q: k = ft,
+    //      ft+4) and 16q + 4ft + {2,3} (step 2q+1); a k-step s of the constant row: columns 8s + 2ft + {0,1}.
+    //      Order of the k-steps: own state (2 NQ), constant row (CS), aggregated state (2 NQ).
+    //   N: n-tile nt = 2q + h, accumulator element j of lane ft <-> output column 16q + 4ft + 2h + j,
+    //      i.e. a lane's 4 NT8 / 2 accumulators of a row are the same columns as its state-row fragments.
+    // B fragment of (k-step s, n-tile nt, lane (g, ft)): b0 = W[krow(s, ft)][ncol(nt, g)], b1 = W[krow(s, ft + 4)][ncol(nt, g)],
+    // stored pre-split for 3xTF32: hi = tf32 part, lo = exact remainder.
+    for (int i = tid; i < KSTEPS * NT8 * 32; i += WS_THREADS) {
+        const int lane = i & 31, nt = (i >> 5) % NT8, st = (i >> 5) / NT8;
+        const int ft = lane & 3, g = lane >> 2;
+        const int n = 16 * (nt >> 1) + 4 * (g >> 1) + 2 * (nt & 1) + (g & 1);
+        float w[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            int row;   // input row of the packed kernel [state(DP) | agg(DP) | cst(CP)]
+            if (st < 2 * NQ) row = 16 * (st >> 1) + 4 * ft + 2 * (st & 1) + h;
+            else if (st < 2 * NQ + CS) { const int c = 8 * (st - 2 * NQ) + 2 * ft + h; row = c < CP ? 2 * DP + c : -1; }
+            else { const int sl = st - 2 * NQ - CS; row = DP + 16 * (sl >> 1) + 4 * ft + 2 * (sl & 1) + h; }
+            w[h] = row >= 0 ? __ldg(p.wpack + net.w_off[0] + row * DP + n) : 0.f;
+        }
+        const float h0 = __uint_as_float(__float_as_uint(w[0]) & 0xffffe000u), h1 = __uint_as_float(__float_as_uint(w[1]) & 0xffffe000u);
+        sW4[i] = make_float4(h0, h1, w[0] - h0, w[1] - h1);
     }
     for (int i = tid; i < DP; i += WS_THREADS) {
         sBias[i] = __ldg(p.wpack + net.b_off[0] + i);
@@ -276,7 +302,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) state_iter_ws_kernel(const Iter
             const int ebase = srow[0];
             const float* lb = land0 + ((size_t)start - a0) * DP + 4 * lig;   // row of tile-relative arc r: lb + r * DP
             const float* sv = sval0 + (size_t)q8 * capc;
-            float* tb = tile0 + (size_t)b * TN * SA + DP + 4 * lig;
+            float* tb = tile0 + (size_t)b * TN * SAG + 4 * lig;
             // segment sums of this lane group's NPG nodes out of the ring, stored order
 #pragma unroll 1
             for (int u = 0; u < NPG; ++u) {
@@ -302,7 +328,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) state_iter_ws_kernel(const Iter
                     acc.x *= sc; acc.y *= sc; acc.z *= sc; acc.w *= sc;
                 }
                 if (p.agg_save && i < nvalid) st4_hint(p.agg_save + (size_t)(n0 + i) * DP + 4 * lig, acc, stream_pol);
-                st4(tb + i * SA, acc);
+                st4(tb + i * SAG, acc);
             }
             mbar_arrive(&bar_free[slot]);
             mbar_arrive(&bar_full[b][cw]);
@@ -315,159 +341,167 @@ __global__ void __launch_bounds__(WS_THREADS, 1) state_iter_ws_kernel(const Iter
         // two MLP groups of 4 warps: group g takes the tiles with sequence number it = g, g+2, ... (= tile buffer g).
         // Inside a group warp w owns nodes [16 w, 16 w + 16) of the tile and all DP outputs: NT8 accumulator fragments.
         // The warps are independent of each other: each one pairs with consume warp w through FULL / EMPTY[g][w].
+        // Own state rows and constant rows never touch shared memory: a lane reads its A fragments straight from global
+        // memory (128-bit, one tile ahead) and keeps them for the convergence test.
         const int mgroup = tid / WS_MLP, mt = tid % WS_MLP;
         const int mwarp = mt >> 5, lane = mt & 31, fg = lane >> 2, ft = lane & 3;   // fragment coordinates (groupID, thread-in-group)
-        const float* bias = sBias;
-        const float* aff_a = sAff;
-        const float* aff_c = sAff + DP;
         const int act = net.act[0], D = net.D;
         const bool affine = !p.bn_train;
         const uint64_t stream_pol = l2_policy_evict_first();
-        double bn_s1[2 * NT8], bn_s2[2 * NT8];
+        double bn_s1[2 * NT8], bn_s2[2 * NT8];     // column 16 (c >> 2) + 4 ft + (c & 3)
 #pragma unroll
         for (int c = 0; c < 2 * NT8; ++c) bn_s1[c] = bn_s2[c] = 0.;
         bool any_moving = false;
-        // own state rows and constant rows of this warp's 16 nodes -> tile buffer (asynchronous; the consume warp only
-        // writes the aggregate columns, so the two never touch the same bytes)
-        float* tb = tile0 + (size_t)mgroup * TN * SA;
-        const int cpq = CP / 4;
-        auto issue_own = [&](long long tile) {
+        const float* tb = tile0 + (size_t)mgroup * TN * SAG + (size_t)(16 * mwarp + fg) * SAG + 4 * ft;   // my row fg of the tile, + 8 SAG: row fg + 8
+
+        float4 xnext[2][NQ];     // own state rows fg, fg + 8: columns 16 q + 4 ft .. + 3
+        float2 cnext[2][2];      // constant rows: columns 8 s + 2 ft, + 1 (CS <= 2)
+        auto load_own = [&](long long tile) {
             const long long n0 = tile * TN;
-            const int nvalid = (int)min((long long)TN, p.N - n0);
 #pragma unroll
-            for (int item = lane; item < WS_SUB * LPN; item += 32) {
-                const int i = WS_SUB * mwarp + item / LPN, l = item % LPN;
-                float* dstp = tb + i * SA + 4 * l;
-                if (i < nvalid) cp_async16(dstp, p.x_in + (size_t)(p.row_offset + n0 + i) * DP + 4 * l);
-                else st4(dstp, make_float4(0.f, 0.f, 0.f, 0.f));
+            for (int h = 0; h < 2; ++h) {
+                const long long n = n0 + 16 * mwarp + fg + 8 * h;
+                const bool valid = n < p.N;
+                const float* xr = p.x_in + (size_t)(p.row_offset + n) * DP + 4 * ft;
+                const float* cr = p.cst + (size_t)n * CP + 2 * ft;
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) xnext[h][q] = valid ? ldg4(xr + 16 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int s2 = 0; s2 < 2; ++s2)
+                    cnext[h][s2] = (valid && 8 * s2 + 2 * ft < CP) ? __ldg(reinterpret_cast<const float2*>(cr + 8 * s2)) : make_float2(0.f, 0.f);
             }
-            for (int item = lane; item < WS_SUB * cpq; item += 32) {
-                const int i = WS_SUB * mwarp + item / cpq, c = item % cpq;
-                float* dstp = tb + i * SA + 2 * DP + 4 * c;
-                if (i < nvalid) cp_async16(dstp, p.cst + (size_t)(n0 + i) * CP + 4 * c);
-                else st4(dstp, make_float4(0.f, 0.f, 0.f, 0.f));
-            }
-            cp_async_commit();
         };
-        if (first + (long long)mgroup * stride < ntiles) issue_own(first + (long long)mgroup * stride);
+        if (first + (long long)mgroup * stride < ntiles) load_own(first + (long long)mgroup * stride);
 
         int it = mgroup;
         for (long long tile = first + (long long)mgroup * stride; tile < ntiles; tile += 2 * stride, it += 2) {
             const long long n0 = tile * TN;
             const int nvalid = (int)min((long long)TN, p.N - n0);
-            mbar_wait(&bar_full[mgroup][mwarp], (it >> 1) & 1);    // aggregates of my 16 nodes are in the buffer
-            cp_async_wait_group<0>();                              // my part of the own / constant rows too ...
-            __syncwarp();                                          // ... and those of the other lanes
+            float4 xcur[2][NQ];
+            float2 ccur[2][2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) xcur[h][q] = xnext[h][q];
+                ccur[h][0] = cnext[h][0]; ccur[h][1] = cnext[h][1];
+            }
+            if (tile + 2 * stride < ntiles) load_own(tile + 2 * stride);   // in flight during this whole tile
 
-            // Dense layer on the tensor cores: 16 x DP outputs per warp, K in steps of 8, 3 x TF32 (fp32-accurate)
+            // Dense layer on the tensor cores: 16 x DP outputs per warp, 3 x TF32 (fp32-accurate)
             float acc[NT8][4];
 #pragma unroll
             for (int nt = 0; nt < NT8; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
-            {
-                const float* arow0 = tb + (16 * mwarp + fg) * SA + ft;       // rows fg and fg + 8 of this warp's block
-                const float* arow1 = arow0 + 8 * SA;
-                const float2* wf = reinterpret_cast<const float2*>(sW) + lane;
-#pragma unroll 3
-                for (int ks = 0; ks < KS; ++ks) {
-                    const int k0 = 8 * ks + ft;
-                    const bool in0 = k0 < KP, in1 = k0 + 4 < KP;             // K padded to a multiple of 8: no read past the inputs
-                    uint32_t ahi[4], alo[4];
-                    split_tf32(in0 ? arow0[8 * ks] : 0.f, ahi[0], alo[0]);
-                    split_tf32(in0 ? arow1[8 * ks] : 0.f, ahi[1], alo[1]);
-                    split_tf32(in1 ? arow0[8 * ks + 4] : 0.f, ahi[2], alo[2]);
-                    split_tf32(in1 ? arow1[8 * ks + 4] : 0.f, ahi[3], alo[3]);
+            auto mma_step = [&](int st, float a0, float a1, float a2, float a3) {   // rows fg, fg+8 x k = ft, ft+4
+                uint32_t ahi[4], alo[4];
+                split_tf32(a0, ahi[0], alo[0]); split_tf32(a1, ahi[1], alo[1]);
+                split_tf32(a2, ahi[2], alo[2]); split_tf32(a3, ahi[3], alo[3]);
+                const float4* wf = sW4 + (size_t)st * NT8 * 32 + lane;
 #pragma unroll
-                    for (int nt = 0; nt < NT8; ++nt) {
-                        const float2 w2 = wf[(ks * NT8 + nt) * 32];
-                        uint32_t bhi[2], blo[2];
-                        split_tf32(w2.x, bhi[0], blo[0]);
-                        split_tf32(w2.y, bhi[1], blo[1]);
-                        mma_tf32_16x8x8(acc[nt], alo, bhi);
-                        mma_tf32_16x8x8(acc[nt], ahi, blo);
-                        mma_tf32_16x8x8(acc[nt], ahi, bhi);
-                    }
+                for (int nt = 0; nt < NT8; ++nt) {
+                    const float4 w = wf[nt * 32];
+                    const uint32_t bhi[2] = {__float_as_uint(w.x), __float_as_uint(w.y)}, blo[2] = {__float_as_uint(w.z), __float_as_uint(w.w)};
+                    mma_tf32_16x8x8(acc[nt], alo, bhi);
+                    mma_tf32_16x8x8(acc[nt], ahi, blo);
+                    mma_tf32_16x8x8(acc[nt], ahi, bhi);
                 }
+            };
+            // own state and constant row: nothing here depends on the gather
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                mma_step(2 * q, xcur[0][q].x, xcur[1][q].x, xcur[0][q].y, xcur[1][q].y);
+                mma_step(2 * q + 1, xcur[0][q].z, xcur[1][q].z, xcur[0][q].w, xcur[1][q].w);
             }
+            mma_step(2 * NQ, ccur[0][0].x, ccur[1][0].x, ccur[0][0].y, ccur[1][0].y);
+            if (CS > 1) mma_step(2 * NQ + 1, ccur[0][1].x, ccur[1][1].x, ccur[0][1].y, ccur[1][1].y);
 
-            // epilogue straight from the accumulator fragments: bias + activation + affine, 8-byte stores (4 lanes = one
-            // 32-byte sector), convergence test reduced over the 4 lanes that share a node row.  The activation is a
-            // compile-time constant inside (one uniform switch per tile instead of one per element)
+            mbar_wait(&bar_full[mgroup][mwarp], (it >> 1) & 1);    // aggregates of my 16 nodes are in the buffer
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                const float4 g0 = ld4(tb + 16 * q), g1 = ld4(tb + 8 * SAG + 16 * q);
+                mma_step(2 * NQ + CS + 2 * q, g0.x, g1.x, g0.y, g1.y);
+                mma_step(2 * NQ + CS + 2 * q + 1, g0.z, g1.z, g0.w, g1.w);
+            }
+            mbar_arrive(&bar_empty[mgroup][mwarp]);                // my rows of the buffer are free again (loads are complete)
+
+            // epilogue straight from the accumulator fragments: bias + activation + affine, one 128-bit store per 16-column
+            // unit and row, convergence test against the old state held in xcur, reduced over the 4 lanes of a row.  The
+            // activation is a compile-time constant inside (one uniform switch per tile instead of one per element)
             auto epilogue = [&](auto act_c) {
                 constexpr int ACT = decltype(act_c)::value;
                 // 1. new state values in place (element-wise, no branches inside: 4 * NT8 independent chains)
 #pragma unroll
-                for (int nt = 0; nt < NT8; ++nt) {
-                    const float2 b2 = *reinterpret_cast<const float2*>(bias + 8 * nt + 2 * ft);
+                for (int q = 0; q < NQ; ++q) {
+                    const float4 b4 = ld4(sBias + 16 * q + 4 * ft);
+                    const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-                    for (int half = 0; half < 2; ++half) {
-                        acc[nt][2 * half] = act_apply(ACT, acc[nt][2 * half] + b2.x);
-                        acc[nt][2 * half + 1] = act_apply(ACT, acc[nt][2 * half + 1] + b2.y);
-                    }
+                    for (int e = 0; e < 4; ++e)
+#pragma unroll
+                        for (int h = 0; h < 2; ++h)
+                            acc[2 * q + (e >> 1)][2 * h + (e & 1)] = act_apply(ACT, acc[2 * q + (e >> 1)][2 * h + (e & 1)] + bb[e]);
                 }
                 if (affine) {
 #pragma unroll
-                    for (int nt = 0; nt < NT8; ++nt) {
-                        const float2 a2 = *reinterpret_cast<const float2*>(aff_a + 8 * nt + 2 * ft);
-                        const float2 c2 = *reinterpret_cast<const float2*>(aff_c + 8 * nt + 2 * ft);
+                    for (int q = 0; q < NQ; ++q) {
+                        const float4 a4 = ld4(sAff + 16 * q + 4 * ft), c4 = ld4(sAff + DP + 16 * q + 4 * ft);
+                        const float aa[4] = {a4.x, a4.y, a4.z, a4.w}, cc[4] = {c4.x, c4.y, c4.z, c4.w};
 #pragma unroll
-                        for (int half = 0; half < 2; ++half) {
-                            acc[nt][2 * half] = fmaf(a2.x, acc[nt][2 * half], c2.x);
-                            acc[nt][2 * half + 1] = fmaf(a2.y, acc[nt][2 * half + 1], c2.y);
-                        }
+                        for (int e = 0; e < 4; ++e)
+#pragma unroll
+                            for (int h = 0; h < 2; ++h)
+                                acc[2 * q + (e >> 1)][2 * h + (e & 1)] = fmaf(aa[e], acc[2 * q + (e >> 1)][2 * h + (e & 1)], cc[e]);
                     }
                 }
                 if (D < DP) {   // padding columns stay zero
 #pragma unroll
-                    for (int nt = 0; nt < NT8; ++nt) {
-                        const int j0 = 8 * nt + 2 * ft;
+                    for (int q = 0; q < NQ; ++q)
 #pragma unroll
-                        for (int half = 0; half < 2; ++half) {
-                            if (j0 >= D) acc[nt][2 * half] = 0.f;
-                            if (j0 + 1 >= D) acc[nt][2 * half + 1] = 0.f;
+                        for (int e = 0; e < 4; ++e)
+                            if (16 * q + 4 * ft + e >= D) acc[2 * q + (e >> 1)][e & 1] = acc[2 * q + (e >> 1)][2 + (e & 1)] = 0.f;
+                }
+                // 2. stores: 16 bytes per lane, 4 lanes = two 32-byte sectors
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int row = 16 * mwarp + fg + 8 * h;
+                    if (row < nvalid) {
+                        float* orow = p.x_out + (size_t)(p.row_offset + n0 + row) * DP + 4 * ft;
+#pragma unroll
+                        for (int q = 0; q < NQ; ++q) {
+                            const float4 y = make_float4(acc[2 * q][2 * h], acc[2 * q][2 * h + 1], acc[2 * q + 1][2 * h], acc[2 * q + 1][2 * h + 1]);
+                            st4_hint(orow + 16 * q, y, stream_pol);
+                            if (p.n_peers > 1) store_to_peers(p, n0 + row, 16 * q + 4 * ft, y);
                         }
                     }
                 }
-                // 2. stores: 8 bytes per lane, 4 lanes = one 32-byte sector
-#pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    const int row = 16 * mwarp + fg + 8 * half;
-                    if (row < nvalid) {
-                        float* orow = p.x_out + (size_t)(p.row_offset + n0 + row) * DP + 2 * ft;
-#pragma unroll
-                        for (int nt = 0; nt < NT8; ++nt)
-                            asm volatile("st.global.L2::cache_hint.v2.f32 [%0], {%1, %2}, %3;" ::"l"(orow + 8 * nt), "f"(acc[nt][2 * half]),
-                                         "f"(acc[nt][2 * half + 1]), "l"(stream_pol) : "memory");
-                        if (p.n_peers > 1)
-#pragma unroll
-                            for (int nt = 0; nt < NT8; ++nt) store_pair_to_peers(p, n0 + row, 8 * nt + 2 * ft, acc[nt][2 * half], acc[nt][2 * half + 1]);
-                    }
-                }
-                // 3. BatchNormalization batch statistics (training) or the convergence test against the old state in the tile
+                // 3. BatchNormalization batch statistics (training) or the convergence test against the old state
                 if (p.bn_train) {
 #pragma unroll
-                    for (int half = 0; half < 2; ++half)
-                        if (16 * mwarp + fg + 8 * half < nvalid)
+                    for (int h = 0; h < 2; ++h)
+                        if (16 * mwarp + fg + 8 * h < nvalid)
 #pragma unroll
-                            for (int nt = 0; nt < NT8; ++nt) {
-                                const float y0 = acc[nt][2 * half], y1 = acc[nt][2 * half + 1];
-                                bn_s1[2 * nt] += y0; bn_s1[2 * nt + 1] += y1;
-                                bn_s2[2 * nt] += (double)y0 * y0; bn_s2[2 * nt + 1] += (double)y1 * y1;
-                            }
+                            for (int q = 0; q < NQ; ++q)
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const float y = acc[2 * q + (e >> 1)][2 * h + (e & 1)];
+                                    bn_s1[4 * q + e] += y;
+                                    bn_s2[4 * q + e] += (double)y * y;
+                                }
                 } else {
 #pragma unroll
-                    for (int half = 0; half < 2; ++half) {
-                        const int row = 16 * mwarp + fg + 8 * half;
+                    for (int h = 0; h < 2; ++h) {
                         float d2 = 0.f, o2 = 0.f;
 #pragma unroll
-                        for (int nt = 0; nt < NT8; ++nt) {
-                            const float2 xo = *reinterpret_cast<const float2*>(tb + row * SA + 8 * nt + 2 * ft);
-                            const float dx = acc[nt][2 * half] - xo.x, dy = acc[nt][2 * half + 1] - xo.y;
-                            d2 += dx * dx + dy * dy;
-                            o2 += xo.x * xo.x + xo.y * xo.y;
+                        for (int q = 0; q < NQ; ++q) {
+                            const float xo[4] = {xcur[h][q].x, xcur[h][q].y, xcur[h][q].z, xcur[h][q].w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float dx = acc[2 * q + (e >> 1)][2 * h + (e & 1)] - xo[e];
+                                d2 = fmaf(dx, dx, d2);
+                                o2 = fmaf(xo[e], xo[e], o2);
+                            }
                         }
                         d2 += __shfl_xor_sync(0xffffffffu, d2, 1); o2 += __shfl_xor_sync(0xffffffffu, o2, 1);
                         d2 += __shfl_xor_sync(0xffffffffu, d2, 2); o2 += __shfl_xor_sync(0xffffffffu, o2, 2);
-                        any_moving |= (row < nvalid) && (sqrtf(d2) > p.thr * sqrtf(o2));
+                        any_moving |= (16 * mwarp + fg + 8 * h < nvalid) && (sqrtf(d2) > p.thr * sqrtf(o2));
                     }
                 }
             };
@@ -479,11 +513,6 @@ __global__ void __launch_bounds__(WS_THREADS, 1) state_iter_ws_kernel(const Iter
                 case GNN_ACT_ELU: epilogue(std::integral_constant<int, GNN_ACT_ELU>{}); break;
                 case GNN_ACT_SOFTPLUS: epilogue(std::integral_constant<int, GNN_ACT_SOFTPLUS>{}); break;
                 default: epilogue(std::integral_constant<int, GNN_ACT_LINEAR>{}); break;
-            }
-            if (tile + 2 * stride < ntiles) {   // this buffer's next tile: fetch its own rows, then hand the rows back
-                __syncwarp();                   // every lane has finished reading the old rows
-                issue_own(tile + 2 * stride);
-                mbar_arrive(&bar_empty[mgroup][mwarp]);
             }
         }
 
@@ -500,7 +529,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) state_iter_ws_kernel(const Iter
             if (lane < 4)
 #pragma unroll
                 for (int c = 0; c < 2 * NT8; ++c) {
-                    const int j = 8 * (c >> 1) + 2 * lane + (c & 1);
+                    const int j = 16 * (c >> 2) + 4 * lane + (c & 3);
                     red[warp][0][j] = bn_s1[c];
                     red[warp][1][j] = bn_s2[c];
                 }

@@ -183,7 +183,7 @@ struct Plan {
 bool ws_applicable(const gnn_graph* g, const gnn_loop_args* a, const NetLayout& lay, int sms) {
     const char* env = getenv("GNN_B200_KERNEL");
     if (env && !strcmp(env, "sym")) return false;
-    if (lay.L != 1 || lay.DP < 16 || lay.DP > 32) return false;
+    if (lay.L != 1 || lay.DP < 16 || lay.DP > 32 || lay.CP > 16) return false;   // (constant row: at most two k-steps in registers)
     if (a->training)
         for (int i = 0; i <= lay.L; ++i) if (lay.drop[i] > 0.f) return false;
     if (env && !strcmp(env, "ws")) return true;
