@@ -47,6 +47,7 @@ struct IterParams {
     int training;
     int scol_cap;
     int ring_slots, slot_rows;   // warp-specialised kernel: landing ring = ring_slots x slot_rows state rows
+    int ws_debug;                // performance experiments only (GNN_B200_WS_DEBUG): 1 no row copies, 2 no segment sums, 4 no mma
     NetLayout net;
 };
 

@@ -42,6 +42,21 @@ __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) 
     const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(dst), "l"(gmem_src));
 }
+__device__ __forceinline__ void cp_async16_if(bool pred, float* smem_dst, const float* gmem_src) {
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p cp.async.cg.shared.global [%0], [%1], 16;\n\t}" ::"r"(dst), "l"(gmem_src), "r"((int)pred));
+}
+// packed fp32 pairs (sm_100 add.f32x2 / fma.rn.f32x2): same IEEE result per element, half the instructions
+__device__ __forceinline__ float4 add4_x2(float4 a, float4 b) {
+    float4 r;
+    asm("{\n\t.reg .b64 a0, a1, b0, b1, r0, r1;\n\t"
+        "mov.b64 a0, {%4, %5};\n\tmov.b64 a1, {%6, %7};\n\tmov.b64 b0, {%8, %9};\n\tmov.b64 b1, {%10, %11};\n\t"
+        "add.rn.f32x2 r0, a0, b0;\n\tadd.rn.f32x2 r1, a1, b1;\n\t"
+        "mov.b64 {%0, %1}, r0;\n\tmov.b64 {%2, %3}, r1;\n\t}"
+        : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+        : "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w));
+    return r;
+}
 template <int N>
 __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
@@ -260,21 +275,16 @@ __global__ void __launch_bounds__(WS_THREADS, 1) state_iter_ws_kernel(const Iter
                 // every landed source row -> ring (asynchronous, no registers): one row per lane group and step
                 float* lb = land0 + (size_t)start * DP + 4 * lig;
                 const int* sc = scol + a0;
-                int r = grp;
-                for (; r < cnt - 3 * NGRP; r += 4 * NGRP) {          // 4 independent index loads, then 4 copies
-                    const int s0 = sc[r], s1 = sc[r + NGRP], s2 = sc[r + 2 * NGRP], s3 = sc[r + 3 * NGRP];
+                const int last = cnt - 1;
+                if (!(p.ws_debug & 1))
+                for (int r = grp; r < cnt; r += 4 * NGRP) {           // 4 independent index loads, then 4 (predicated) copies
+                    const int r1 = r + NGRP, r2 = r + 2 * NGRP, r3 = r + 3 * NGRP;
+                    const int s0 = sc[r], s1 = sc[min(r1, last)], s2 = sc[min(r2, last)], s3 = sc[min(r3, last)];
                     cp_async16(lb + (size_t)r * DP, xl + (size_t)s0 * DP);
-                    cp_async16(lb + (size_t)(r + NGRP) * DP, xl + (size_t)s1 * DP);
-                    cp_async16(lb + (size_t)(r + 2 * NGRP) * DP, xl + (size_t)s2 * DP);
-                    cp_async16(lb + (size_t)(r + 3 * NGRP) * DP, xl + (size_t)s3 * DP);
+                    cp_async16_if(r1 < cnt, lb + (size_t)r1 * DP, xl + (size_t)s1 * DP);
+                    cp_async16_if(r2 < cnt, lb + (size_t)r2 * DP, xl + (size_t)s2 * DP);
+                    cp_async16_if(r3 < cnt, lb + (size_t)r3 * DP, xl + (size_t)s3 * DP);
                 }
-                if (r < cnt - NGRP) {
-                    const int s0 = sc[r], s1 = sc[r + NGRP];
-                    cp_async16(lb + (size_t)r * DP, xl + (size_t)s0 * DP);
-                    cp_async16(lb + (size_t)(r + NGRP) * DP, xl + (size_t)s1 * DP);
-                    r += 2 * NGRP;
-                }
-                if (r < cnt) cp_async16(lb + (size_t)r * DP, xl + (size_t)sc[r] * DP);
                 cp_async_mbar_arrive(&bar_landed[slot]);
                 slot += 2;
                 ++m;
@@ -305,7 +315,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) state_iter_ws_kernel(const Iter
             float* tb = tile0 + (size_t)b * TN * SAG + 4 * lig;
             // segment sums of this lane group's NPG nodes out of the ring, stored order
 #pragma unroll 1
-            for (int u = 0; u < NPG; ++u) {
+            for (int u = 0; u < ((p.ws_debug & 2) ? 0 : NPG); ++u) {
                 const int i = WS_SUB * cw + grpw * NPG + u;
                 const int r0 = srow[i] - ebase, r1 = srow[i + 1] - ebase;
                 float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -315,7 +325,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) state_iter_ws_kernel(const Iter
                 for (; r < rl; ++r) {
                     const float4 v = ld4(lb + (ptrdiff_t)r * DP);
                     if (HAS_VAL) acc = fma4(sv[r], v, acc);
-                    else acc = add4(acc, v);
+                    else acc = add4_x2(acc, v);
                 }
                 for (; r < r1; ++r) {   // arcs that did not get ring rows: direct loads (rare, very dense sub-tiles)
                     const int s = __ldg(p.col + ebase + r);
@@ -392,6 +402,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) state_iter_ws_kernel(const Iter
 #pragma unroll
             for (int nt = 0; nt < NT8; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
             auto mma_step = [&](int st, float a0, float a1, float a2, float a3) {   // rows fg, fg+8 x k = ft, ft+4
+                if (p.ws_debug & 4) return;
                 uint32_t ahi[4], alo[4];
                 split_tf32(a0, ahi[0], alo[0]); split_tf32(a1, ahi[1], alo[1]);
                 split_tf32(a2, ahi[2], alo[2]); split_tf32(a3, ahi[3], alo[3]);

@@ -327,7 +327,8 @@ extern "C" int gnn_state_loop_forward(const gnn_graph* g, const gnn_mlp* net, co
     memset(&p, 0, sizeof(p));
     p.rowptr = g->rowptr; p.col = g->col; p.val = plan.has_val ? g->val : nullptr; p.N = N; p.row_offset = a->row_offset;
     p.cst = w.cst; p.wpack = w.wpack; p.k_ptr = kptr; p.thr = a->threshold; p.bn_partial = w.bn_partial;
-    p.bn_train = bn_train; p.seed = a->seed; p.training = a->training; p.scol_cap = plan.scol_cap; p.ring_slots = plan.ring_slots; p.slot_rows = plan.slot_rows; p.net = lay;
+    p.bn_train = bn_train; p.seed = a->seed; p.training = a->training; p.scol_cap = plan.scol_cap; p.ring_slots = plan.ring_slots; p.slot_rows = plan.slot_rows;
+    { const char* dbg = getenv("GNN_B200_WS_DEBUG"); p.ws_debug = dbg ? atoi(dbg) : 0; } p.net = lay;
     p.n_peers = a->n_global > 0 ? a->n_peers : 0; p.rank = a->rank; p.peer_mask = a->peer_mask;
     BnApplyKernel bn_apply = kernel_set(lay.DP)->bn_apply;
 
