@@ -368,7 +368,7 @@ def main():
         pass
     peak_gbs = float(peaks.get('hbm_gbs', 6650.0))
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
-    roofline = {'bound': 'hbm', 'kernel': 'state_iter_kernel<32,false,128,128>', 'achieved': achieved, 'peak': peak_gbs, 'unit': 'GB/s',
+    roofline = {'bound': 'hbm', 'kernel': _native.last_forward_kernel(), 'achieved': achieved, 'peak': peak_gbs, 'unit': 'GB/s',
                 'frac': achieved / peak_gbs, 'traffic': None, 'peak_source': 'MEASURED_PEAKS.json' if peaks else 'fallback 6650 GB/s',
                 'algorithmic_bytes_per_launch': alg_bytes, 'bytes_per_arc_update': alg_bytes / E, 'ms_per_launch': kernel_ms}
     traffic_file = os.path.join(ROOT, 'profiles', 'traffic_bytes_per_launch.json')

@@ -62,7 +62,7 @@ EXCHANGE_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int32, C.c_int64, C.c_int64)
 # every symbol include/gnn_b200.h declares (tests check that the library exports all of them)
 EXPORTED_SYMBOLS = ['gnn_last_error', 'gnn_abi_version', 'gnn_device_info', 'gnn_csr_build', 'gnn_spmm',
                     'gnn_state_loop_workspace_bytes', 'gnn_state_loop_layout', 'gnn_state_loop_forward', 'gnn_state_loop_backward',
-                    'gnn_launch_count', 'gnn_profile_iterations', 'gnn_profile_last_iterations']
+                    'gnn_launch_count', 'gnn_profile_iterations', 'gnn_profile_last_iterations', 'gnn_last_forward_kernel']
 
 
 def library_path() -> str: return _LIB_PATH
@@ -77,6 +77,7 @@ def lib() -> C.CDLL:
                                f'(make -C gnn_tf_2.x_b200/csrc). There is no CPU fallback.')
         l = C.CDLL(_LIB_PATH)
         l.gnn_last_error.restype = C.c_char_p
+        l.gnn_last_forward_kernel.restype = C.c_char_p
         l.gnn_abi_version.restype = C.c_int
         l.gnn_launch_count.restype = C.c_int64
         l.gnn_launch_count.argtypes = [C.c_int32]
@@ -123,6 +124,10 @@ def _stream(device) -> int:
 
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
+
+
+def last_forward_kernel() -> str:
+    return lib().gnn_last_forward_kernel().decode()
 
 
 def profile_iterations(enable: bool) -> None:

@@ -19,6 +19,7 @@ struct IterProfile {
     bool pending = false;
 };
 static IterProfile g_profile;
+static char g_last_kernel[96] = "";
 
 struct DeviceInfo {
     int sms = 0, smem_optin = 0;
@@ -332,6 +333,8 @@ extern "C" int gnn_state_loop_forward(const gnn_graph* g, const gnn_mlp* net, co
     p.n_peers = a->n_global > 0 ? a->n_peers : 0; p.rank = a->rank; p.peer_mask = a->peer_mask;
     BnApplyKernel bn_apply = kernel_set(lay.DP)->bn_apply;
 
+    snprintf(g_last_kernel, sizeof(g_last_kernel), plan.ws ? "state_iter_ws_kernel<%d,%s>" : "state_iter_kernel<%d,%s,%d,%d>", lay.DP,
+             plan.has_val ? "true" : "false", plan.ts.tn, plan.ts.nt);
     if (g_profile.enabled) {
         GNN_CUDA(cudaEventRecord(g_profile.begin, stream));
         g_profile.launches = 0;
@@ -387,6 +390,8 @@ extern "C" int gnn_state_loop_layout(const gnn_graph* g, const gnn_mlp* net, con
     if (state_bytes) *state_bytes = w.slab * 4;
     return GNN_OK;
 }
+
+extern "C" const char* gnn_last_forward_kernel(void) { return g_last_kernel; }
 
 extern "C" int gnn_profile_iterations(int32_t enable) {
     if (enable && !g_profile.begin) {

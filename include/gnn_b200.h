@@ -198,6 +198,8 @@ int64_t gnn_launch_count(int32_t reset);
  * iteration launches enqueued between the two events (launches that found the loop stopped return at once). */
 int gnn_profile_iterations(int32_t enable);
 int gnn_profile_last_iterations(float* elapsed_ms, int32_t* launches);
+/* name of the iteration kernel the last gnn_state_loop_forward call launched ("" before the first call) */
+const char* gnn_last_forward_kernel(void);
 
 #ifdef __cplusplus
 }
