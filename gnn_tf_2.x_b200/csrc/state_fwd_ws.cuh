@@ -4,7 +4,7 @@
 // microbenchmark on B200 (scripts/gather_microbench.cu) needs >= 1000 rows in flight per SM to reach the L2/HBM limit;
 // the symmetric kernel (state_fwd.cuh) holds its rows in registers and cannot have that many in flight next to the MLP.
 // Here the rows land in shared memory through cp.async (no registers, deep queue) and THREE roles run concurrently in
-// one persistent CTA of 512 threads per SM.  Work unit of the gather: a SUB-TILE of 16 nodes (= one m16 mma block);
+// one persistent CTA of 768 threads per SM (register budgets re-split per role with setmaxnreg).  Work unit of the gather: a SUB-TILE of 16 nodes (= one m16 mma block);
 // 4 sub-tiles = one 64-node tile.  The landing zone is ONE ring of rows; every sub-tile owns a contiguous range of it
 // from the moment its copies are issued until its segment sums are done, so almost all of the ring is in flight at any
 // time (a ring of two whole-tile stages spends half of its life waiting to be consumed).
@@ -18,8 +18,9 @@
 //   consume warps (4): warp c owns sub-tile c of every tile.  wait LANDED -> segment sums out of shared memory in stored
 //                      order (deterministic, no atomics) into rows 16c..16c+15 of tile[j&1] -> mbarrier FULL[j&1][c] for
 //                      MLP warp c of group j&1, mbarrier FREE for the issue warps
-//   MLP warps     (8): two groups of 4, even / odd tiles; warp c owns rows 16c..16c+15: own state / constant rows by
-//                      cp.async, wait FULL -> Dense layer on the tensor cores (mma.sync m16n8k8, 3xTF32 = fp32-accurate)
+//   MLP warps    (12): three groups of 4, tiles it = g, g+3, ...; warp c owns rows 16c..16c+15: own state / constant rows
+//                      straight from global memory as mma A fragments, wait FULL -> Dense layer on the tensor cores
+//                      (mma.sync m16n8k8, 3xTF32 = fp32-accurate)
 //                      -> bias / activation / affine -> store of the new state + convergence test (+ BatchNormalization
 //                      batch statistics when training) -> mbarrier EMPTY[j&1][c].  No block-wide barrier in the loop.
 //
@@ -76,15 +77,16 @@ __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) 
 constexpr int WS_TN = 64;          // nodes per tile
 constexpr int WS_SUB = 16;         // nodes per sub-tile (one m16 block, one consume warp, one MLP warp)
 constexpr int WS_NSUB = WS_TN / WS_SUB;
-constexpr int WS_MLP = 128;        // threads of ONE MLP group (4 warps); two groups: even / odd tiles
-constexpr int WS_MLP_ALL = 256;    // both MLP groups (warps 0-7)
-constexpr int WS_CONS = 128;       // consume threads (warps 8-11)
-constexpr int WS_ISSUE = 256;      // issue threads (warps 12-19): two groups of 4 warps, even / odd sub-tiles
+constexpr int WS_MLP = 128;        // threads of ONE MLP group (4 warps)
+constexpr int WS_MLP_GROUPS = 3;   // group g takes the tiles it = g, g+3, ... (tile buffer g)
+constexpr int WS_MLP_ALL = WS_MLP * WS_MLP_GROUPS;   // warps 0-11
+constexpr int WS_CONS = 128;       // consume threads (warps 12-15)
+constexpr int WS_ISSUE = 256;      // issue threads (warps 16-23): two groups of 4 warps, even / odd sub-tiles
 constexpr int WS_ISSUE_GRP = 128;
-constexpr int WS_THREADS = 640;
-// registers per thread after the roles split (setmaxnreg): 640 x 96 at launch -> MLP 152, consume 64, issue 48
-constexpr int WS_REGS_MLP = 152, WS_REGS_CONS = 64, WS_REGS_ISSUE = 48;
-static_assert(8 * (WS_REGS_MLP - 96) <= 8 * (96 - WS_REGS_ISSUE) + 4 * (96 - WS_REGS_CONS),
+constexpr int WS_THREADS = 768;
+// registers per thread after the roles split (setmaxnreg): 768 x 80 at launch -> MLP 104, consume 64, issue 48
+constexpr int WS_REGS_LAUNCH = 80, WS_REGS_MLP = 104, WS_REGS_CONS = 64, WS_REGS_ISSUE = 48;
+static_assert(4 * WS_MLP_GROUPS * (WS_REGS_MLP - WS_REGS_LAUNCH) <= 8 * (WS_REGS_LAUNCH - WS_REGS_ISSUE) + 4 * (WS_REGS_LAUNCH - WS_REGS_CONS),
               "setmaxnreg.inc only draws on what this CTA's own warps released (spare registers of the SM do not count)");
 constexpr int WS_SLOTS = 16;       // sub-tiles in flight at most (mbarrier slots of the ring)
 constexpr int WS_ROWQ = 8;         // row-pointer / scale buffers (tiles)
@@ -118,7 +120,7 @@ static inline size_t ws_weight_floats(const NetLayout& lay) { return (size_t)ws_
 
 // shared-memory footprint (bytes): `ring` landing rows (slots x rows per slot), arc-index capacity `capc` per tile
 static inline size_t ws_smem_bytes(const NetLayout& lay, int ring, int capc, bool has_val) {
-    size_t fl = ws_weight_floats(lay) + 2 * (size_t)WS_TN * ws_tile_stride(lay.DP) + (size_t)ring * lay.DP + WS_ROWQ * 68 + WS_ROWQ * WS_TN +
+    size_t fl = ws_weight_floats(lay) + WS_MLP_GROUPS * (size_t)WS_TN * ws_tile_stride(lay.DP) + (size_t)ring * lay.DP + WS_ROWQ * 68 + WS_ROWQ * WS_TN +
                 3 * (size_t)capc + (has_val ? WS_ROWQ * (size_t)capc : 0);   // tiles x2, ring, row pointers / scales, arc indices x3, weights
     return fl * 4;
 }
@@ -147,14 +149,15 @@ __global__ void __launch_bounds__(WS_THREADS, 1) state_iter_ws_kernel(const Iter
     float4* sW4 = reinterpret_cast<float4*>(smem);      // [KSTEPS][NT8][32 lanes]: B fragments {hi b0, hi b1, lo b0, lo b1}
     float* sBias = smem + (size_t)KSTEPS * NT8 * 128;   // [DP]
     float* sAff = sBias + DP;                           // a[DP], c[DP]
-    float* tile0 = sAff + 2 * DP;                       // [2][TN][SAG]: aggregated states
-    float* land0 = tile0 + 2 * TN * SAG;                // [nslot][slotcap][DP]
+    float* tile0 = sAff + 2 * DP;                       // [WS_MLP_GROUPS][TN][SAG]: aggregated states
+    float* land0 = tile0 + WS_MLP_GROUPS * TN * SAG;    // [nslot][slotcap][DP]
     int* srow0 = reinterpret_cast<int*>(land0 + (size_t)nslot * slotcap * DP);   // [WS_ROWQ][68]
     float* sscale0 = reinterpret_cast<float*>(srow0 + WS_ROWQ * 68);     // [WS_ROWQ][TN]
     int* scol0 = reinterpret_cast<int*>(sscale0 + WS_ROWQ * TN);         // [3][capc]
     float* sval0 = reinterpret_cast<float*>(scol0 + 3 * capc);           // [WS_ROWQ][capc] (HAS_VAL; read by the consume warps)
     __shared__ int s_flag;
-    __shared__ __align__(8) uint64_t bar_landed[WS_SLOTS], bar_free[WS_SLOTS], bar_cols[3], bar_full[2][WS_NSUB], bar_empty[2][WS_NSUB];
+    __shared__ __align__(8) uint64_t bar_landed[WS_SLOTS], bar_free[WS_SLOTS], bar_cols[3], bar_full[WS_MLP_GROUPS][WS_NSUB], bar_empty[WS_MLP_GROUPS][WS_NSUB];
+    __shared__ double bn_acc[4 * WS_MLP_GROUPS][2][DP];   // BatchNormalization batch statistics, one private row per MLP warp
 
     // The mma K and N indices are ours to permute as long as A, B and C agree.  Both are laid out so that a lane's fragment
     // elements are CONTIGUOUS in memory (128-bit loads / stores, whole 32-byte sectors per 4 lanes):
@@ -186,11 +189,12 @@ __global__ void __launch_bounds__(WS_THREADS, 1) state_iter_ws_kernel(const Iter
         sAff[i] = __ldg(p.wpack + net.aff_off + i);
         sAff[DP + i] = __ldg(p.wpack + net.aff_off + DP + i);
     }
+    for (int i = tid; i < 4 * WS_MLP_GROUPS * 2 * DP; i += WS_THREADS) (&bn_acc[0][0][0])[i] = 0.;
     if (tid == 0) {
         s_flag = 0;
         for (int i = 0; i < WS_SLOTS; ++i) { mbar_init(&bar_landed[i], WS_ISSUE_GRP); mbar_init(&bar_free[i], 32); }
         for (int i = 0; i < 3; ++i) mbar_init(&bar_cols[i], WS_ISSUE);
-        for (int i = 0; i < 2 * WS_NSUB; ++i) { mbar_init(&bar_full[0][0] + i, 32); mbar_init(&bar_empty[0][0] + i, 32); }
+        for (int i = 0; i < WS_MLP_GROUPS * WS_NSUB; ++i) { mbar_init(&bar_full[0][0] + i, 32); mbar_init(&bar_empty[0][0] + i, 32); }
     }
     __syncthreads();
 
@@ -299,8 +303,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) state_iter_ws_kernel(const Iter
         const int lane = tid & 31, grpw = lane / LPN, lig = lane % LPN;
         const uint64_t stream_pol = l2_policy_evict_first();
         int it = 0, slot = cw, phase = 0;                   // slot / mbarrier phase of sub-tile j = 4 it + cw (nslot >= 4)
+        int b = 0, round = 0;                               // tile buffer it % WS_MLP_GROUPS, it / WS_MLP_GROUPS
         for (long long tile = first; tile < ntiles; tile += stride, ++it) {
-            const int b = it & 1, q8 = it & (WS_ROWQ - 1);
+            const int q8 = it & (WS_ROWQ - 1);
             const long long n0 = tile * TN;
             const int nvalid = (int)min((long long)TN, p.N - n0);
             const int* srow = srow0 + q8 * 68;
@@ -308,7 +313,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) state_iter_ws_kernel(const Iter
             int a0, cnt;
             sub_range(srow, cw, a0, cnt);
             const int start = slot * slotcap;
-            if (it >= 2) mbar_wait(&bar_empty[b][cw], ((it >> 1) - 1) & 1);   // MLP warp cw of group b is done with tile it-2
+            if (round > 0) mbar_wait(&bar_empty[b][cw], (round - 1) & 1);   // MLP warp cw of group b is done with tile it - WS_MLP_GROUPS
             const int ebase = srow[0];
             const float* lb = land0 + ((size_t)start - a0) * DP + 4 * lig;   // row of tile-relative arc r: lb + r * DP
             const float* sv = sval0 + (size_t)q8 * capc;
@@ -344,6 +349,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) state_iter_ws_kernel(const Iter
             mbar_arrive(&bar_full[b][cw]);
             slot += WS_NSUB;
             if (slot >= nslot) { slot -= nslot; phase ^= 1; }
+            if (++b == WS_MLP_GROUPS) { b = 0; ++round; }
         }
     } else {
         // ============================================= MLP WARPS ==============================================
@@ -352,22 +358,24 @@ __global__ void __launch_bounds__(WS_THREADS, 1) state_iter_ws_kernel(const Iter
         // Inside a group warp w owns nodes [16 w, 16 w + 16) of the tile and all DP outputs: NT8 accumulator fragments.
         // The warps are independent of each other: each one pairs with consume warp w through FULL / EMPTY[g][w].
         // Own state rows and constant rows never touch shared memory: a lane reads its A fragments straight from global
-        // memory (128-bit, one tile ahead) and keeps them for the convergence test.
+        // memory (128-bit, in flight while it waits for the aggregates) and keeps them for the convergence test.
         const int mgroup = tid / WS_MLP, mt = tid % WS_MLP;
         const int mwarp = mt >> 5, lane = mt & 31, fg = lane >> 2, ft = lane & 3;   // fragment coordinates (groupID, thread-in-group)
         const int act = net.act[0], D = net.D;
         const bool affine = !p.bn_train;
         const uint64_t stream_pol = l2_policy_evict_first();
-        double bn_s1[2 * NT8], bn_s2[2 * NT8];     // column 16 (c >> 2) + 4 ft + (c & 3)
-#pragma unroll
-        for (int c = 0; c < 2 * NT8; ++c) bn_s1[c] = bn_s2[c] = 0.;
         bool any_moving = false;
         const float* tb = tile0 + (size_t)mgroup * TN * SAG + (size_t)(16 * mwarp + fg) * SAG + 4 * ft;   // my row fg of the tile, + 8 SAG: row fg + 8
+        double* bn_mine = &bn_acc[tid >> 5][0][0];   // [2][DP], private to this warp
 
-        float4 xnext[2][NQ];     // own state rows fg, fg + 8: columns 16 q + 4 ft .. + 3
-        float2 cnext[2][2];      // constant rows: columns 8 s + 2 ft, + 1 (CS <= 2)
-        auto load_own = [&](long long tile) {
+        int round = 0;
+        for (long long tile = first + (long long)mgroup * stride; tile < ntiles; tile += WS_MLP_GROUPS * stride, ++round) {
             const long long n0 = tile * TN;
+            const int nvalid = (int)min((long long)TN, p.N - n0);
+            // own state rows fg, fg + 8 (columns 16 q + 4 ft .. + 3) and constant rows (columns 8 s + 2 ft, + 1; CS <= 2):
+            // in flight while this warp waits for the aggregates and multiplies them
+            float4 xcur[2][NQ];
+            float2 ccur[2][2];
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const long long n = n0 + 16 * mwarp + fg + 8 * h;
@@ -375,27 +383,11 @@ __global__ void __launch_bounds__(WS_THREADS, 1) state_iter_ws_kernel(const Iter
                 const float* xr = p.x_in + (size_t)(p.row_offset + n) * DP + 4 * ft;
                 const float* cr = p.cst + (size_t)n * CP + 2 * ft;
 #pragma unroll
-                for (int q = 0; q < NQ; ++q) xnext[h][q] = valid ? ldg4(xr + 16 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int q = 0; q < NQ; ++q) xcur[h][q] = valid ? ldg4(xr + 16 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                 for (int s2 = 0; s2 < 2; ++s2)
-                    cnext[h][s2] = (valid && 8 * s2 + 2 * ft < CP) ? __ldg(reinterpret_cast<const float2*>(cr + 8 * s2)) : make_float2(0.f, 0.f);
+                    ccur[h][s2] = (valid && 8 * s2 + 2 * ft < CP) ? __ldg(reinterpret_cast<const float2*>(cr + 8 * s2)) : make_float2(0.f, 0.f);
             }
-        };
-        if (first + (long long)mgroup * stride < ntiles) load_own(first + (long long)mgroup * stride);
-
-        int it = mgroup;
-        for (long long tile = first + (long long)mgroup * stride; tile < ntiles; tile += 2 * stride, it += 2) {
-            const long long n0 = tile * TN;
-            const int nvalid = (int)min((long long)TN, p.N - n0);
-            float4 xcur[2][NQ];
-            float2 ccur[2][2];
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-#pragma unroll
-                for (int q = 0; q < NQ; ++q) xcur[h][q] = xnext[h][q];
-                ccur[h][0] = cnext[h][0]; ccur[h][1] = cnext[h][1];
-            }
-            if (tile + 2 * stride < ntiles) load_own(tile + 2 * stride);   // in flight during this whole tile
 
             // Dense layer on the tensor cores: 16 x DP outputs per warp, 3 x TF32 (fp32-accurate)
             float acc[NT8][4];
@@ -416,16 +408,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) state_iter_ws_kernel(const Iter
                     mma_tf32_16x8x8(acc[nt], ahi, bhi);
                 }
             };
-            // own state and constant row: nothing here depends on the gather
-#pragma unroll
-            for (int q = 0; q < NQ; ++q) {
-                mma_step(2 * q, xcur[0][q].x, xcur[1][q].x, xcur[0][q].y, xcur[1][q].y);
-                mma_step(2 * q + 1, xcur[0][q].z, xcur[1][q].z, xcur[0][q].w, xcur[1][q].w);
-            }
-            mma_step(2 * NQ, ccur[0][0].x, ccur[1][0].x, ccur[0][0].y, ccur[1][0].y);
-            if (CS > 1) mma_step(2 * NQ + 1, ccur[0][1].x, ccur[1][1].x, ccur[0][1].y, ccur[1][1].y);
-
-            mbar_wait(&bar_full[mgroup][mwarp], (it >> 1) & 1);    // aggregates of my 16 nodes are in the buffer
+            mbar_wait(&bar_full[mgroup][mwarp], round & 1);        // aggregates of my 16 nodes are in the buffer
 #pragma unroll
             for (int q = 0; q < NQ; ++q) {
                 const float4 g0 = ld4(tb + 16 * q), g1 = ld4(tb + 8 * SAG + 16 * q);
@@ -433,6 +416,14 @@ __global__ void __launch_bounds__(WS_THREADS, 1) state_iter_ws_kernel(const Iter
                 mma_step(2 * NQ + CS + 2 * q + 1, g0.z, g1.z, g0.w, g1.w);
             }
             mbar_arrive(&bar_empty[mgroup][mwarp]);                // my rows of the buffer are free again (loads are complete)
+            // own state and constant row
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                mma_step(2 * q, xcur[0][q].x, xcur[1][q].x, xcur[0][q].y, xcur[1][q].y);
+                mma_step(2 * q + 1, xcur[0][q].z, xcur[1][q].z, xcur[0][q].w, xcur[1][q].w);
+            }
+            mma_step(2 * NQ, ccur[0][0].x, ccur[1][0].x, ccur[0][0].y, ccur[1][0].y);
+            if (CS > 1) mma_step(2 * NQ + 1, ccur[0][1].x, ccur[1][1].x, ccur[0][1].y, ccur[1][1].y);
 
             // epilogue straight from the accumulator fragments: bias + activation + affine, one 128-bit store per 16-column
             // unit and row, convergence test against the old state held in xcur, reduced over the 4 lanes of a row.  The
@@ -485,17 +476,25 @@ __global__ void __launch_bounds__(WS_THREADS, 1) state_iter_ws_kernel(const Iter
                 }
                 // 3. BatchNormalization batch statistics (training) or the convergence test against the old state
                 if (p.bn_train) {
+                    // column sums over this warp's 16 rows: fp32 over the 2 rows of a lane and the 8 lanes that share its
+                    // columns (xor 4, 8, 16), then fp64 accumulation in the warp's private shared-memory row
+                    const bool v0 = 16 * mwarp + fg < nvalid, v1 = 16 * mwarp + fg + 8 < nvalid;
 #pragma unroll
-                    for (int h = 0; h < 2; ++h)
-                        if (16 * mwarp + fg + 8 * h < nvalid)
+                    for (int q = 0; q < NQ; ++q)
 #pragma unroll
-                            for (int q = 0; q < NQ; ++q)
+                        for (int e = 0; e < 4; ++e) {
+                            const float y0 = v0 ? acc[2 * q + (e >> 1)][e & 1] : 0.f, y1 = v1 ? acc[2 * q + (e >> 1)][2 + (e & 1)] : 0.f;
+                            float s1 = y0 + y1, s2 = fmaf(y0, y0, y1 * y1);
 #pragma unroll
-                                for (int e = 0; e < 4; ++e) {
-                                    const float y = acc[2 * q + (e >> 1)][2 * h + (e & 1)];
-                                    bn_s1[4 * q + e] += y;
-                                    bn_s2[4 * q + e] += (double)y * y;
-                                }
+                            for (int off = 4; off < 32; off <<= 1) {
+                                s1 += __shfl_xor_sync(0xffffffffu, s1, off);
+                                s2 += __shfl_xor_sync(0xffffffffu, s2, off);
+                            }
+                            if (fg == 0) {
+                                bn_mine[16 * q + 4 * ft + e] += (double)s1;
+                                bn_mine[DP + 16 * q + 4 * ft + e] += (double)s2;
+                            }
+                        }
                 } else {
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
@@ -528,27 +527,12 @@ __global__ void __launch_bounds__(WS_THREADS, 1) state_iter_ws_kernel(const Iter
         }
 
         if (p.bn_train) {
-            // lanes with the same ft hold the same columns: reduce over fg (xor 4, 8, 16), then over the 8 MLP warps
-#pragma unroll
-            for (int c = 0; c < 2 * NT8; ++c)
-                for (int off = 4; off < 32; off <<= 1) {
-                    bn_s1[c] += __shfl_xor_sync(0xffffffffu, bn_s1[c], off);
-                    bn_s2[c] += __shfl_xor_sync(0xffffffffu, bn_s2[c], off);
-                }
-            __shared__ double red[8][2][DP];
-            const int warp = tid >> 5;
-            if (lane < 4)
-#pragma unroll
-                for (int c = 0; c < 2 * NT8; ++c) {
-                    const int j = 16 * (c >> 2) + 4 * lane + (c & 3);
-                    red[warp][0][j] = bn_s1[c];
-                    red[warp][1][j] = bn_s2[c];
-                }
+            // per-CTA partial sums: the MLP warps' private rows added in warp order (deterministic)
             named_bar_sync(GNN_BAR_MLP_ALL, WS_MLP_ALL);
             if (tid < 2 * DP) {
                 const int which = tid / DP, j = tid % DP;
                 double sum = 0.;
-                for (int w = 0; w < 8; ++w) sum += red[w][which][j];
+                for (int w = 0; w < 4 * WS_MLP_GROUPS; ++w) sum += bn_acc[w][which][j];
                 p.bn_partial[(size_t)blockIdx.x * 2 * DP + which * DP + j] = sum;
             }
         } else {

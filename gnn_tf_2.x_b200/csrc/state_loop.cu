@@ -210,7 +210,7 @@ int make_plan(const gnn_graph* g, const gnn_mlp* net, const gnn_loop_args* a, Pl
         long long capc_want = avg * 3 / 2;
         if (g->max_block16_arcs > 0) capc_want = std::min<long long>(capc_want, (long long)WS_NSUB * g->max_block16_arcs);   // no tile has more
         const int capc = (int)std::min<long long>(4096, std::max<long long>(128, (capc_want + 15) / 16 * 16));
-        const size_t budget = (size_t)di.smem_optin - 5120;   // static shared memory of the kernel + slack
+        const size_t budget = (size_t)di.smem_optin - 7168;   // static shared memory of the kernel (mbarriers, BN accumulators) + slack
         const size_t fixed = ws_smem_bytes(lay, 0, capc, plan->has_val);
         const int ring = fixed < budget ? (int)std::min<size_t>(4096, (budget - fixed) / ((size_t)lay.DP * 4)) : 0;
         // slots of the ring: one sub-tile (16 nodes) each.  When the caller knows the densest block of 16 rows the slot
