@@ -236,7 +236,7 @@ def main():
     ap.add_argument('--nodes', type=int, default=1_000_000)
     ap.add_argument('--arcs', type=int, default=10_000_000)
     ap.add_argument('--max-iter', type=int, default=50)
-    ap.add_argument('--cpu-iterations', type=int, default=3, help='iterations of the workload timed on the CPU port')
+    ap.add_argument('--cpu-iterations', type=int, default=40, help='iterations of the workload timed on the CPU port')
     ap.add_argument('--skip-train', action='store_true')
     ap.add_argument('--skip-cpu', action='store_true')
     args = ap.parse_args()
