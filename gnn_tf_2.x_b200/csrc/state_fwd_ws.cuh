@@ -78,15 +78,15 @@ constexpr int WS_TN = 64;          // nodes per tile
 constexpr int WS_SUB = 16;         // nodes per sub-tile (one m16 block, one consume warp, one MLP warp)
 constexpr int WS_NSUB = WS_TN / WS_SUB;
 constexpr int WS_MLP = 128;        // threads of ONE MLP group (4 warps)
-constexpr int WS_MLP_GROUPS = 3;   // group g takes the tiles it = g, g+3, ... (tile buffer g)
-constexpr int WS_MLP_ALL = WS_MLP * WS_MLP_GROUPS;   // warps 0-11
-constexpr int WS_CONS = 128;       // consume threads (warps 12-15)
+constexpr int WS_MLP_GROUPS = 2;   // group g takes the tiles it = g, g+2, ... (tile buffer g)
+constexpr int WS_MLP_ALL = WS_MLP * WS_MLP_GROUPS;   // warps 0-7
+constexpr int WS_CONS = 256;       // consume threads (warps 8-15): group g (4 warps) takes the tiles it = g, g+2, ...; warp c sub-tile c
 constexpr int WS_ISSUE = 256;      // issue threads (warps 16-23): two groups of 4 warps, even / odd sub-tiles
 constexpr int WS_ISSUE_GRP = 128;
 constexpr int WS_THREADS = 768;
 // registers per thread after the roles split (setmaxnreg): 768 x 80 at launch -> MLP 104, consume 64, issue 48
 constexpr int WS_REGS_LAUNCH = 80, WS_REGS_MLP = 104, WS_REGS_CONS = 64, WS_REGS_ISSUE = 48;
-static_assert(4 * WS_MLP_GROUPS * (WS_REGS_MLP - WS_REGS_LAUNCH) <= 8 * (WS_REGS_LAUNCH - WS_REGS_ISSUE) + 4 * (WS_REGS_LAUNCH - WS_REGS_CONS),
+static_assert(4 * WS_MLP_GROUPS * (WS_REGS_MLP - WS_REGS_LAUNCH) <= 8 * (WS_REGS_LAUNCH - WS_REGS_ISSUE) + 8 * (WS_REGS_LAUNCH - WS_REGS_CONS),
               "setmaxnreg.inc only draws on what this CTA's own warps released (spare registers of the SM do not count)");
 constexpr int WS_SLOTS = 16;       // sub-tiles in flight at most (mbarrier slots of the ring)
 constexpr int WS_ROWQ = 8;         // row-pointer / scale buffers (tiles)
@@ -299,12 +299,18 @@ __global__ void __launch_bounds__(WS_THREADS, 1) state_iter_ws_kernel(const Iter
     } else if (tid >= WS_MLP_ALL) {
         // =========================================== CONSUME WARPS =============================================
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(WS_REGS_CONS));
-        const int cw = (tid - WS_MLP_ALL) >> 5;             // this warp's sub-tile of every tile
+        const int cwarp = (tid - WS_MLP_ALL) >> 5;
+        const int cw = cwarp & 3, cg = cwarp >> 2;          // sub-tile cw of the tiles it = cg, cg+2, ...: the warp pairs with MLP warp
+                                                            // cw of group cg (tile buffer cg) and, nslot being 8 or 16, is the only
+                                                            // consumer of its ring slots
         const int lane = tid & 31, grpw = lane / LPN, lig = lane % LPN;
         const uint64_t stream_pol = l2_policy_evict_first();
-        int it = 0, slot = cw, phase = 0;                   // slot / mbarrier phase of sub-tile j = 4 it + cw (nslot >= 4)
-        int b = 0, round = 0;                               // tile buffer it % WS_MLP_GROUPS, it / WS_MLP_GROUPS
-        for (long long tile = first; tile < ntiles; tile += stride, ++it) {
+        const int b = cg;
+        const int slot_shift = nslot == 8 ? 3 : 4;
+        int round = 0;                                      // it / 2
+        for (int it = cg; tile_at(it) < ntiles; it += 2, ++round) {
+            const long long tile = tile_at(it);
+            const int j = WS_NSUB * it + cw, slot = j & (nslot - 1), phase = (j >> slot_shift) & 1;
             const int q8 = it & (WS_ROWQ - 1);
             const long long n0 = tile * TN;
             const int nvalid = (int)min((long long)TN, p.N - n0);
@@ -347,9 +353,6 @@ __global__ void __launch_bounds__(WS_THREADS, 1) state_iter_ws_kernel(const Iter
             }
             mbar_arrive(&bar_free[slot]);
             mbar_arrive(&bar_full[b][cw]);
-            slot += WS_NSUB;
-            if (slot >= nslot) { slot -= nslot; phase ^= 1; }
-            if (++b == WS_MLP_GROUPS) { b = 0; ++round; }
         }
     } else {
         // ============================================= MLP WARPS ==============================================

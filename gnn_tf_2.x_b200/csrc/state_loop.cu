@@ -220,15 +220,20 @@ int make_plan(const gnn_graph* g, const gnn_mlp* net, const gnn_loop_args* a, Pl
         long long want = g->max_block16_arcs > 0 ? std::min<long long>(g->max_block16_arcs, std::max<long long>(32, avg_sub * 3 / 2))
                                                  : avg_sub * 9 / 8;
         const int slot_rows = (int)((want + 3) / 4 * 4);
-        const int slots = std::min(WS_SLOTS, ring / slot_rows) & ~1;   // even: a slot belongs to one issue group
-        if (slots >= 4) {
+        // 8 or 16 slots (a slot then always serves the same consume warp and the same issue group); when not even 8 average
+        // sub-tiles fit, the slots shrink and the consume warps read the excess arcs directly
+        int slot_rows_fit = slot_rows;
+        int slots = ring / slot_rows >= 16 ? 16 : 8;
+        if (ring / slot_rows < 8) slot_rows_fit = (ring / 8) & ~3;
+        if (slot_rows_fit < 16 || slot_rows_fit * 2 < avg_sub) slots = 0;
+        if (slots >= 8) {
             plan->ws = true;
             plan->kernel = ks->iter_ws[plan->has_val ? 1 : 0];
             plan->ts = TileShape{WS_TN, WS_THREADS};
             plan->scol_cap = capc;
             plan->ring_slots = slots;
-            plan->slot_rows = slot_rows;
-            plan->smem = ws_smem_bytes(lay, slots * slot_rows, capc, plan->has_val);
+            plan->slot_rows = slot_rows_fit;
+            plan->smem = ws_smem_bytes(lay, slots * slot_rows_fit, capc, plan->has_val);
             int occ = 0;
             GNN_TRY(kernel_occupancy((const void*)plan->kernel, WS_THREADS, plan->smem, &occ));
             const long long ntiles = (g->n_nodes + WS_TN - 1) / WS_TN;
