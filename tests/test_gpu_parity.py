@@ -331,9 +331,16 @@ def test_ws_and_symmetric_kernels_agree(monkeypatch):
     """ both kernels sum the arcs in stored order; the MLP differs only in rounding (tensor-core 3xTF32 vs fp32 FMA) """
     _require_gpu()
     case = random_case(seed=710, n_nodes=30000, n_arcs=240000, NL=3, AL=1, DS=32, act='selu', max_iter=5, threshold=0.0, bn=True)
+    from gnn_b200 import _native
     monkeypatch.setenv('GNN_B200_KERNEL', 'ws')
     a = run_cuda(case, training=False)
+    assert _native.last_forward_kernel() == 'state_iter_ws_kernel<32,false>'
     monkeypatch.setenv('GNN_B200_KERNEL', 'sym')
     b = run_cuda(case, training=False)
+    assert _native.last_forward_kernel().startswith('state_iter_kernel<32,false')
+    monkeypatch.delenv('GNN_B200_KERNEL')
+    c = run_cuda(case, training=False)      # the planner's own choice at this size: the warp-specialised kernel, bit-identical
+    assert _native.last_forward_kernel() == 'state_iter_ws_kernel<32,false>'
+    np.testing.assert_array_equal(a['state'], c['state'])
     assert a['k'] == b['k']
     assert rel_err(a["state"], b["state"]) < 2e-5   # 3xTF32 tensor-core product vs sequential fp32 FMA
