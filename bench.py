@@ -239,6 +239,7 @@ def main():
     ap.add_argument('--cpu-iterations', type=int, default=40, help='iterations of the workload timed on the CPU port')
     ap.add_argument('--skip-train', action='store_true')
     ap.add_argument('--skip-cpu', action='store_true')
+    ap.add_argument('--skip-variant', action='store_true', help='skip the side-by-side forward run on the other source distribution')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -312,7 +313,19 @@ def main():
     if world > 1:
         with ClockSampler(local_rank) as clocks:
             result = dist_graph.bench_partitioned(g_host, wl, build_gnn, args, device, rank, world)
+        variant = None
+        if not args.skip_variant and args.workload in ('c4u', 'c4l'):
+            other = 'c4l' if args.workload == 'c4u' else 'c4u'
+            del g_host
+            wl2 = make_workload(other, args.nodes, args.arcs)
+            g2 = GraphObject(arcs=wl2['arcs'], nodes=wl2['nodes'], targets=wl2['targets'], problem_based='n', aggregation_mode='average',
+                             _endpoints=(wl2['src'], wl2['dst']))
+            wl.update(x0=wl2['x0'], ws=wl2['ws'], wo=wl2['wo'])
+            r2 = dist_graph.bench_partitioned(g2, wl2, build_gnn, args, device, rank, world, with_e2e=False)
+            variant = {'workload': other + (': sources within +-2048 of the destination (boundary rows travel)' if other == 'c4l' else ': uniform sources'),
+                       'value': r2['value'], 'ms_per_step': r2['ms_per_step'], 'iterations': r2['iterations'], 'partition': r2['partition']}
         if rank == 0:
+            result['source_distribution_variant'] = variant
             config['partition'] = result.pop('partition')
             result.update({'metric': metric, 'unit': 'arc-updates/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(3, args.warmup),
                            'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
@@ -406,6 +419,34 @@ def main():
         train = {'value': E * float(kt[-1]) / (ms_train * 1e-3), 'unit': 'arc-updates/s (forward+backward+Adam)', 'ms_per_step': ms_train,
                  'epoch_time_s': ms_train * 1e-3, 'k': float(kt[-1])}
 
+    # --- the other source distribution, forward loop only (U and L side by side) --------------------------
+    variant = None
+    if not args.skip_variant and args.workload in ('c4u', 'c4l'):
+        other = 'c4l' if args.workload == 'c4u' else 'c4u'
+        del gt, g_host
+        torch.cuda.empty_cache()
+        wl2 = make_workload(other, args.nodes, args.arcs)
+        g2 = GraphObject(arcs=wl2['arcs'], nodes=wl2['nodes'], targets=wl2['targets'], problem_based='n', aggregation_mode='average',
+                         _endpoints=(wl2['src'], wl2['dst']))
+        gt2 = GraphTensor.fromGraphObject(g2, device=device)
+        gnn.initial_state = torch.as_tensor(wl2['x0'], device=device)
+        ks2 = []
+
+        def fwd2():
+            with torch.no_grad():
+                k, state, out = gnn.Loop(gt2, training=False)
+            ks2.append(k)
+
+        ms2 = timed(fwd2, args.steps, 3)
+        _native.profile_iterations(True)
+        fwd2()
+        ms_k2, n2 = _native.profile_last_iterations()
+        _native.profile_iterations(False)
+        variant = {'workload': other + (': sources within +-2048 of the destination' if other == 'c4l' else ': uniform sources'),
+                   'value': wl2['E'] * float(ks2[-1]) / (ms2 * 1e-3), 'ms_per_step': ms2, 'iterations': float(ks2[-1]),
+                   'ms_per_launch': ms_k2 / max(n2, 1), 'roofline_frac': alg_bytes / (ms_k2 / max(n2, 1) * 1e-3) / 1e9 / peak_gbs}
+        del gt2, g2
+
     # --- CPU baseline: oracle port on the host cores, bounded sample ----------------------------------------------
     cpu = None
     if not args.skip_cpu:
@@ -417,7 +458,8 @@ def main():
     print(json.dumps({'metric': metric, 'value': value, 'unit': 'arc-updates/s', 'n_gpus': 1, 'steps': args.steps, 'warmup': max(3, args.warmup),
                       'ms_per_step': ms_fwd, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32',
                       'data': 'synthetic', 'config': config, 'iterations': k_fwd, 'e2e': e2e, 'gpu_launches': int(launches_fwd),
-                      'roofline': roofline, 'train': train, 'cpu_baseline': cpu, 'clocks': clocks.summary()}))
+                      'roofline': roofline, 'train': train, 'source_distribution_variant': variant, 'cpu_baseline': cpu,
+                      'clocks': clocks.summary()}))
 
 
 if __name__ == '__main__':

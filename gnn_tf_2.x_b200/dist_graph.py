@@ -229,7 +229,7 @@ def partitioned_loop(gnn, part: GraphPartition, x0: Optional[torch.Tensor] = Non
 # ---------------------------------------------------------------------------------------------------------------------
 # bench.py leg for N > 1 (strong scaling of the C4 graph)
 # ---------------------------------------------------------------------------------------------------------------------
-def bench_partitioned(g_host, wl, build_gnn, args, device, rank, world):
+def bench_partitioned(g_host, wl, build_gnn, args, device, rank, world, with_e2e: bool = True):
     from . import _native
     gnn = build_gnn()
     part = GraphPartition(g_host, rank, world, device=device)
@@ -259,6 +259,14 @@ def bench_partitioned(g_host, wl, build_gnn, args, device, rank, world):
     launches = _native.launch_count() * args.steps // (args.steps + warm)
     k_fwd = float(ks[-1])
 
+    halo = part.halo.bytes_received_per_exchange(128) if part.halo is not None else 0
+    partition = {'ranks': world, 'rows_per_rank': part.n_local,
+                 'exchange': ('fused NVLink peer stores in the iteration kernel' if part.fused else 'NCCL ') +
+                             (' (every row to every peer)' if part.halo.use_allgather else ' (boundary rows only)'),
+                 'halo_bytes_received_per_iteration_per_rank': int(halo)}
+    if not with_e2e:
+        return {'value': E * k_fwd / (ms_fwd * 1e-3), 'ms_per_step': ms_fwd, 'iterations': k_fwd, 'gpu_launches': int(launches), 'partition': partition}
+
     # e2e: host buffers of the local rows -> device (CSR build included) -> loop -> local outputs back on the host
     g_host.pin_host_buffers()
     x0_host = torch.from_numpy(wl['x0']).pin_memory()
@@ -273,11 +281,7 @@ def bench_partitioned(g_host, wl, build_gnn, args, device, rank, world):
 
     ms_e2e = timed(e2e_step, max(1, args.steps // 2), 1)
     local_bytes = g_host.host_bytes() + x0_host.numel() * 4      # every rank receives the whole COO and selects on the device
-    halo = part.halo.bytes_received_per_exchange(128) if part.halo is not None else 0
     return {'value': E * k_fwd / (ms_fwd * 1e-3), 'ms_per_step': ms_fwd, 'iterations': k_fwd, 'gpu_launches': int(launches),
             'e2e': {'value': E * k_fwd / (ms_e2e * 1e-3), 'unit': 'arc-updates/s', 'ms_per_step': ms_e2e,
                     'h2d_bytes_per_step': int(local_bytes), 'd2h_bytes_per_step': int(held[-1].numel() * 4)},
-            'partition': {'ranks': world, 'rows_per_rank': part.n_local,
-                          'exchange': ('fused NVLink peer stores in the iteration kernel' if part.fused else 'NCCL ') +
-                                      (' (every row to every peer)' if part.halo.use_allgather else ' (boundary rows only)'),
-                          'halo_bytes_received_per_iteration_per_rank': int(halo)}}
+            'partition': partition}
