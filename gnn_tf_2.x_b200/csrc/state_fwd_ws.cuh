@@ -91,6 +91,12 @@ static_assert(4 * WS_MLP_GROUPS * (WS_REGS_MLP - WS_REGS_LAUNCH) <= 8 * (WS_REGS
 constexpr int WS_SLOTS = 16;       // sub-tiles in flight at most (mbarrier slots of the ring)
 constexpr int WS_ROWQ = 8;         // row-pointer / scale buffers (tiles)
 
+#ifndef GNN_WS_SLEEP_MLP
+#define GNN_WS_SLEEP_MLP 256
+#endif
+#ifndef GNN_WS_SLEEP_CONS
+#define GNN_WS_SLEEP_CONS 96
+#endif
 // mbarrier (shared memory, CTA scope)
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
@@ -102,13 +108,18 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void cp_async_mbar_arrive(uint64_t* bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
 }
+// SLEEP_NS > 0: back off between polls.  A spinning warp polls about once per 30 cycles and takes issue slots from the warps
+// it is waiting for; the roles with slack (MLP, consume) sleep, the issue warps (the critical role) spin.
+template <int SLEEP_NS = 0>
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     const unsigned addr = (unsigned)__cvta_generic_to_shared(bar);
     uint32_t done;
-    do {
+    for (;;) {
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(done) : "r"(addr), "r"(parity) : "memory");
-    } while (!done);
+        if (done) break;
+        if (SLEEP_NS > 0) __nanosleep(SLEEP_NS);
+    }
 }
 
 // aggregate tile row stride (floats): rows g and g+1 of a quarter-warp's 128-bit fragment loads fall in different bank halves
@@ -315,11 +326,11 @@ __global__ void __launch_bounds__(WS_THREADS, 1) state_iter_ws_kernel(const Iter
             const long long n0 = tile * TN;
             const int nvalid = (int)min((long long)TN, p.N - n0);
             const int* srow = srow0 + q8 * 68;
-            mbar_wait(&bar_landed[slot], phase);            // rows of the sub-tile, row pointers (and weights) of the tile
+            mbar_wait<GNN_WS_SLEEP_CONS>(&bar_landed[slot], phase);            // rows of the sub-tile, row pointers (and weights) of the tile
             int a0, cnt;
             sub_range(srow, cw, a0, cnt);
             const int start = slot * slotcap;
-            if (round > 0) mbar_wait(&bar_empty[b][cw], (round - 1) & 1);   // MLP warp cw of group b is done with tile it - WS_MLP_GROUPS
+            if (round > 0) mbar_wait<GNN_WS_SLEEP_CONS>(&bar_empty[b][cw], (round - 1) & 1);   // MLP warp cw of group b is done with tile it - WS_MLP_GROUPS
             const int ebase = srow[0];
             const float* lb = land0 + ((size_t)start - a0) * DP + 4 * lig;   // row of tile-relative arc r: lb + r * DP
             const float* sv = sval0 + (size_t)q8 * capc;
@@ -411,7 +422,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) state_iter_ws_kernel(const Iter
                     mma_tf32_16x8x8(acc[nt], ahi, bhi);
                 }
             };
-            mbar_wait(&bar_full[mgroup][mwarp], round & 1);        // aggregates of my 16 nodes are in the buffer
+            mbar_wait<GNN_WS_SLEEP_MLP>(&bar_full[mgroup][mwarp], round & 1);        // aggregates of my 16 nodes are in the buffer
 #pragma unroll
             for (int q = 0; q < NQ; ++q) {
                 const float4 g0 = ld4(tb + 16 * q), g1 = ld4(tb + 8 * SAG + 16 * q);
