@@ -77,19 +77,25 @@ static __global__ void pack_cst_kernel(const float* __restrict__ nodes, const fl
 }
 
 // X0 = pad(x0); go[0] = any_n( ||x0_n - 1|| > thr * ||1|| ) && max_iter > 0   (GNN.py:266, :202-220)
+// one thread per (node, 4 columns): coalesced reads of x0, 128-bit stores; the DP/4 lanes of a node are adjacent
 static __global__ void init_state_kernel(const float* __restrict__ x0, long long N, int D, int DP, float thr, int max_iter,
                                   float* __restrict__ X0, int* __restrict__ go0) {
-    const long long n = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    bool moving = false;
+    const int LPN = DP >> 2;                       // power of two <= 32
+    const long long item = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long n = item / LPN;
+    const int j0 = 4 * (int)(item % LPN);
+    float d2 = 0.f;
     if (n < N) {
-        float d2 = 0.f;
-        for (int j = 0; j < DP; ++j) {
-            const float v = j < D ? x0[n * D + j] : 0.f;
-            X0[n * DP + j] = v;
-            if (j < D) d2 += (v - 1.f) * (v - 1.f);
+        float v[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            v[c] = j0 + c < D ? __ldg(x0 + n * D + j0 + c) : 0.f;
+            if (j0 + c < D) d2 += (v[c] - 1.f) * (v[c] - 1.f);
         }
-        moving = sqrtf(d2) > thr * sqrtf((float)D);
+        st4(X0 + n * DP + j0, make_float4(v[0], v[1], v[2], v[3]));
     }
+    for (int off = 1; off < LPN; off <<= 1) d2 += __shfl_xor_sync(0xffffffffu, d2, off);
+    const bool moving = n < N && sqrtf(d2) > thr * sqrtf((float)D);
     const int block_moving = __syncthreads_or(moving ? 1 : 0);
     if (max_iter > 0 && block_moving && threadIdx.x == 0 && *reinterpret_cast<volatile int*>(go0) == 0) atomicOr(go0, 1);
 }
@@ -162,6 +168,10 @@ static __global__ void finalize_kernel(const int* __restrict__ k_ptr, const floa
     const float* src = base + (size_t)(ring ? (k % ring) : k) * slab_floats;
     const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (idx == 0 && k_out) *k_out = (float)k;
+    if (D == DP) {                                  // no padding: 128-bit copy (4 elements per thread)
+        if (4 * idx < N * D) st4(x_out + 4 * idx, ldg4(src + 4 * idx));
+        return;
+    }
     if (idx >= N * D) return;
     const long long n = idx / D;
     const int j = (int)(idx % D);

@@ -326,7 +326,7 @@ extern "C" int gnn_state_loop_forward(const gnn_graph* g, const gnn_mlp* net, co
         GNN_LAUNCH_CHECK();
     }
     // the initial state is replicated: every rank pads all rows and evaluates the first condition on all of them
-    init_state_kernel<<<(unsigned)ceil_div(NGLOB, 128), 128, 0, stream>>>(a->x0, NGLOB, lay.D, lay.DP, a->threshold, a->max_iter, w.X, go);
+    init_state_kernel<<<(unsigned)ceil_div(NGLOB * (lay.DP / 4), 256), 256, 0, stream>>>(a->x0, NGLOB, lay.D, lay.DP, a->threshold, a->max_iter, w.X, go);
     GNN_LAUNCH_CHECK();
 
     IterParams p;
