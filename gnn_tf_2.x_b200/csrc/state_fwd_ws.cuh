@@ -4,25 +4,26 @@
 // microbenchmark on B200 (scripts/gather_microbench.cu) needs >= 1000 rows in flight per SM to reach the L2/HBM limit;
 // the symmetric kernel (state_fwd.cuh) holds its rows in registers and cannot have that many in flight next to the MLP.
 // Here the rows land in shared memory through cp.async (no registers, deep queue) and THREE roles run concurrently in
-// one persistent CTA of 768 threads per SM (register budgets re-split per role with setmaxnreg).  Work unit of the gather: a SUB-TILE of 16 nodes (= one m16 mma block);
-// 4 sub-tiles = one 64-node tile.  The landing zone is ONE ring of rows; every sub-tile owns a contiguous range of it
-// from the moment its copies are issued until its segment sums are done, so almost all of the ring is in flight at any
-// time (a ring of two whole-tile stages spends half of its life waiting to be consumed).
+// one persistent CTA of 768 threads per SM (register budgets re-split per role with setmaxnreg).  Work unit of the
+// gather: a SUB-TILE of 16 nodes (= one m16 mma block); 4 sub-tiles = one 64-node tile.  The landing zone is a ring of
+// 8 or 16 slots, one sub-tile each: a slot is in flight from the moment its copies are issued until its segment sums are
+// done (a ring of two whole-tile stages spends half of its life waiting to be consumed).
 //
-//   issue warps   (4): never wait for data.  Per tile: arc sources / row pointers of tile j+2 -> shared memory
-//                      (cp.async, completion -> mbarrier COLS); per sub-tile: allocate ring rows (waiting for the oldest
-//                      sub-tiles to be released when the ring is full), one 16-byte cp.async per lane for every source
-//                      row; completion of all of them arrives on the sub-tile's mbarrier LANDED
-//                      (cp.async.mbarrier.arrive.noinc).  They block only on the LSU queue: the memory pipe is fed
-//                      continuously.
-//   consume warps (4): warp c owns sub-tile c of every tile.  wait LANDED -> segment sums out of shared memory in stored
-//                      order (deterministic, no atomics) into rows 16c..16c+15 of tile[j&1] -> mbarrier FULL[j&1][c] for
-//                      MLP warp c of group j&1, mbarrier FREE for the issue warps
-//   MLP warps    (12): three groups of 4, tiles it = g, g+3, ...; warp c owns rows 16c..16c+15: own state / constant rows
-//                      straight from global memory as mma A fragments, wait FULL -> Dense layer on the tensor cores
-//                      (mma.sync m16n8k8, 3xTF32 = fp32-accurate)
+//   issue warps   (8): two groups of 4 (even / odd sub-tiles); never wait for data.  Per tile: arc sources / row pointers
+//                      of tile j+2 -> shared memory (cp.async, completion -> mbarrier COLS); per sub-tile: wait for its
+//                      slot (mbarrier FREE), one 16-byte cp.async per lane for every source row; completion of all of
+//                      them arrives on the slot's mbarrier LANDED (cp.async.mbarrier.arrive.noinc).  They block only on
+//                      the LSU queue: the memory pipe is fed continuously.
+//   consume warps (8): two groups of 4 (even / odd tiles); warp c owns sub-tile c.  wait LANDED -> segment sums out of
+//                      shared memory in stored order (deterministic, no atomics, packed add.f32x2) into rows 16c..16c+15
+//                      of aggregate tile g -> mbarrier FULL[g][c] for MLP warp c of group g, mbarrier FREE for the slot
+//   MLP warps     (8): two groups of 4 (even / odd tiles), paired 1:1 with the consume warps; warp c owns rows
+//                      16c..16c+15: own state / constant rows straight from global memory as mma A fragments, wait FULL
+//                      -> Dense layer on the tensor cores (mma.sync m16n8k8, 3xTF32 = fp32-accurate) -> mbarrier EMPTY
 //                      -> bias / activation / affine -> store of the new state + convergence test (+ BatchNormalization
-//                      batch statistics when training) -> mbarrier EMPTY[j&1][c].  No block-wide barrier in the loop.
+//                      batch statistics when training).  No block-wide barrier in the loop.
+// Every ring slot and every tile row has exactly one producer warp set and one consumer warp: nobody can observe an
+// mbarrier two phases late (a parity wait cannot tell phase k from phase k+2).
 //
 // Used for single-Dense-layer state nets (what the reference builds by default) with padded state width 16..32 and no
 // active dropout; every other case runs the symmetric kernel.
