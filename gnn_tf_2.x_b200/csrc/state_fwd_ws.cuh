@@ -91,6 +91,7 @@ static_assert(4 * WS_MLP_GROUPS * (WS_REGS_MLP - WS_REGS_LAUNCH) <= 8 * (WS_REGS
               "setmaxnreg.inc only draws on what this CTA's own warps released (spare registers of the SM do not count)");
 constexpr int WS_SLOTS = 16;       // sub-tiles in flight at most (mbarrier slots of the ring)
 constexpr int WS_ROWQ = 8;         // row-pointer / scale buffers (tiles)
+constexpr int WS_COLPAD = 128;     // slack behind each arc-source buffer: the batched index loads may run past the last arc
 
 #ifndef GNN_WS_SLEEP_MLP
 #define GNN_WS_SLEEP_MLP 256
@@ -133,7 +134,7 @@ static inline size_t ws_weight_floats(const NetLayout& lay) { return (size_t)ws_
 // shared-memory footprint (bytes): `ring` landing rows (slots x rows per slot), arc-index capacity `capc` per tile
 static inline size_t ws_smem_bytes(const NetLayout& lay, int ring, int capc, bool has_val) {
     size_t fl = ws_weight_floats(lay) + WS_MLP_GROUPS * (size_t)WS_TN * ws_tile_stride(lay.DP) + (size_t)ring * lay.DP + WS_ROWQ * 68 + WS_ROWQ * WS_TN +
-                3 * (size_t)capc + (has_val ? WS_ROWQ * (size_t)capc : 0);   // tiles x2, ring, row pointers / scales, arc indices x3, weights
+                3 * (size_t)(capc + WS_COLPAD) + (has_val ? WS_ROWQ * (size_t)capc : 0);   // tiles x2, ring, row pointers / scales, arc indices x3, weights
     return fl * 4;
 }
 
@@ -166,7 +167,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) state_iter_ws_kernel(const Iter
     int* srow0 = reinterpret_cast<int*>(land0 + (size_t)nslot * slotcap * DP);   // [WS_ROWQ][68]
     float* sscale0 = reinterpret_cast<float*>(srow0 + WS_ROWQ * 68);     // [WS_ROWQ][TN]
     int* scol0 = reinterpret_cast<int*>(sscale0 + WS_ROWQ * TN);         // [3][capc]
-    float* sval0 = reinterpret_cast<float*>(scol0 + 3 * capc);           // [WS_ROWQ][capc] (HAS_VAL; read by the consume warps)
+    float* sval0 = reinterpret_cast<float*>(scol0 + 3 * (capc + WS_COLPAD));           // [WS_ROWQ][capc] (HAS_VAL; read by the consume warps)
     __shared__ int s_flag;
     __shared__ __align__(8) uint64_t bar_landed[WS_SLOTS], bar_free[WS_SLOTS], bar_cols[3], bar_full[WS_MLP_GROUPS][WS_NSUB], bar_empty[WS_MLP_GROUPS][WS_NSUB];
     __shared__ double bn_acc[4 * WS_MLP_GROUPS][2][DP];   // BatchNormalization batch statistics, one private row per MLP warp
@@ -237,7 +238,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) state_iter_ws_kernel(const Iter
             const int q8 = seq & (WS_ROWQ - 1), q3 = seq % 3;
             const int ecount = min(e1 - e0, capc);
             for (int r = gt; r < ecount; r += WS_ISSUE) {
-                cp_async4(scol0 + (size_t)q3 * capc + r, p.col + e0 + r);
+                cp_async4(scol0 + (size_t)q3 * (capc + WS_COLPAD) + r, p.col + e0 + r);
                 if (HAS_VAL) cp_async4(sval0 + (size_t)q8 * capc + r, p.val + e0 + r);
             }
             for (int i = gt; i <= TN; i += WS_ISSUE) cp_async4(srow0 + q8 * 68 + i, p.rowptr + min(n0 + i, p.N));
@@ -280,7 +281,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) state_iter_ws_kernel(const Iter
             if (t3 < ntiles) tile_arcs(t3, e0, e1);
             mbar_wait(&bar_cols[it % 3], (it / 3) & 1);              // indices / row pointers of tile it have landed
             const int* srow = srow0 + (it & (WS_ROWQ - 1)) * 68;
-            const int* scol = scol0 + (size_t)(it % 3) * capc;
+            const int* scol = scol0 + (size_t)(it % 3) * (capc + WS_COLPAD);
             const float* xl = p.x_in + 4 * lig;
 #pragma unroll 1
             for (int c = ig; c < WS_NSUB; c += 2) {
@@ -291,15 +292,18 @@ __global__ void __launch_bounds__(WS_THREADS, 1) state_iter_ws_kernel(const Iter
                 // every landed source row -> ring (asynchronous, no registers): one row per lane group and step
                 float* lb = land0 + (size_t)start * DP + 4 * lig;
                 const int* sc = scol + a0;
-                const int last = cnt - 1;
+                // 4 independent index loads, then 4 copies (the last three predicated).  Index loads past the sub-tile's last
+                // arc stay inside the padded buffer and their values are not used.
+                static_assert(3 * NGRP < WS_COLPAD, "index loads run at most 3 NGRP entries past the last arc");
                 if (!(p.ws_debug & 1))
-                for (int r = grp; r < cnt; r += 4 * NGRP) {           // 4 independent index loads, then 4 (predicated) copies
-                    const int r1 = r + NGRP, r2 = r + 2 * NGRP, r3 = r + 3 * NGRP;
-                    const int s0 = sc[r], s1 = sc[min(r1, last)], s2 = sc[min(r2, last)], s3 = sc[min(r3, last)];
-                    cp_async16(lb + (size_t)r * DP, xl + (size_t)s0 * DP);
-                    cp_async16_if(r1 < cnt, lb + (size_t)r1 * DP, xl + (size_t)s1 * DP);
-                    cp_async16_if(r2 < cnt, lb + (size_t)r2 * DP, xl + (size_t)s2 * DP);
-                    cp_async16_if(r3 < cnt, lb + (size_t)r3 * DP, xl + (size_t)s3 * DP);
+                for (int r = grp; r < cnt; r += 4 * NGRP) {
+                    const int* si = sc + r;
+                    float* di = lb + (size_t)r * DP;
+                    const int s0 = si[0], s1 = si[NGRP], s2 = si[2 * NGRP], s3 = si[3 * NGRP];
+                    cp_async16(di, xl + (size_t)s0 * DP);
+                    cp_async16_if(r + NGRP < cnt, di + NGRP * DP, xl + (size_t)s1 * DP);
+                    cp_async16_if(r + 2 * NGRP < cnt, di + 2 * NGRP * DP, xl + (size_t)s2 * DP);
+                    cp_async16_if(r + 3 * NGRP < cnt, di + 3 * NGRP * DP, xl + (size_t)s3 * DP);
                 }
                 cp_async_mbar_arrive(&bar_landed[slot]);
                 slot += 2;
