@@ -110,6 +110,18 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void cp_async_mbar_arrive(uint64_t* bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
 }
+// the same operations on a precomputed shared-memory address (saves the generic -> shared conversion per call)
+__device__ __forceinline__ unsigned smem_u32(const void* ptr) { return (unsigned)__cvta_generic_to_shared(ptr); }
+__device__ __forceinline__ void cp_async_mbar_arrive_u32(unsigned addr) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_u32(unsigned addr, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    } while (!done);
+}
 // SLEEP_NS > 0: back off between polls.  A spinning warp polls about once per 30 cycles and takes issue slots from the warps
 // it is waiting for; the roles with slack (MLP, consume) sleep, the issue warps (the critical role) spin.
 template <int SLEEP_NS = 0>
@@ -256,6 +268,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) state_iter_ws_kernel(const Iter
         // nslot is even: slot j % nslot has the parity of the sub-tile, i.e. a slot is only ever used by ONE issue group,
         // which is therefore the only thread set waiting on its FREE barrier (never more than one phase behind)
         int slot = ig, m = 0;                   // slot (= j % nslot) of this group's next sub-tile; sub-tiles issued so far
+        const unsigned landed_u32 = smem_u32(bar_landed), free_u32 = smem_u32(bar_free);
         int wphase = 0;                         // FREE phase to wait for; flips each time `slot` wraps
         const int per_round = nslot / 2;        // this group's slots
 
@@ -283,11 +296,22 @@ __global__ void __launch_bounds__(WS_THREADS, 1) state_iter_ws_kernel(const Iter
             const int* srow = srow0 + (it & (WS_ROWQ - 1)) * 68;
             const int* scol = scol0 + (size_t)(it % 3) * (capc + WS_COLPAD);
             const float* xl = p.x_in + 4 * lig;
-#pragma unroll 1
-            for (int c = ig; c < WS_NSUB; c += 2) {
-                int a0, cnt;
-                sub_range(srow, c, a0, cnt);
-                if (m >= per_round) mbar_wait(&bar_free[slot], wphase);   // the slot's previous sub-tile has been consumed
+            // arc ranges of this group's two sub-tiles (c = ig, ig + 2): five independent loads, one latency
+            int a0s[2], cnts[2];
+            {
+                const int eb = srow[0];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int c = ig + 2 * h;
+                    const int lo = srow[WS_SUB * c] - eb, hi = min(srow[WS_SUB * c + WS_SUB] - eb, capc);
+                    a0s[h] = lo;
+                    cnts[h] = max(0, min(hi - lo, slotcap));
+                }
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int a0 = a0s[h], cnt = cnts[h];
+                if (m >= per_round) mbar_wait_u32(free_u32 + 8 * slot, wphase);   // the slot's previous sub-tile has been consumed
                 const int start = slot * slotcap;
                 // every landed source row -> ring (asynchronous, no registers): one row per lane group and step
                 float* lb = land0 + (size_t)start * DP + 4 * lig;
@@ -305,7 +329,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) state_iter_ws_kernel(const Iter
                     cp_async16_if(r + 2 * NGRP < cnt, di + 2 * NGRP * DP, xl + (size_t)s2 * DP);
                     cp_async16_if(r + 3 * NGRP < cnt, di + 3 * NGRP * DP, xl + (size_t)s3 * DP);
                 }
-                cp_async_mbar_arrive(&bar_landed[slot]);
+                cp_async_mbar_arrive_u32(landed_u32 + 8 * slot);
                 slot += 2;
                 ++m;
                 if (slot >= nslot) { slot -= nslot; if (m > per_round) wphase ^= 1; }
