@@ -397,8 +397,8 @@ def main():
     def e2e_step():
         gnn.initial_state = x0_host.to(device, non_blocking=True)
         out = gnn(g_host)
-        d2h_holder.append(out.cpu())
-        if len(d2h_holder) > 2: d2h_holder.pop(0)
+        if not d2h_holder: d2h_holder.append(torch.empty(out.shape, dtype=out.dtype).pin_memory())   # page-locked result buffer
+        d2h_holder[0].copy_(out, non_blocking=True)      # the timed region ends with a synchronize: the result is on the host
 
     ms_e2e = timed(e2e_step, args.steps, 1)
     e2e = {'value': E * k_fwd / (ms_e2e * 1e-3), 'unit': 'arc-updates/s', 'ms_per_step': ms_e2e, 'h2d_bytes_per_step': int(h2d),

@@ -192,7 +192,7 @@ class GNNnodeBased(BaseClass):
 
     def _state_and_inputs(self, g: GraphTensor):
         """ prologue of Loop (GNN.py:257-268) """
-        labels = g.arcs[:, 2:]
+        labels = g.arc_labels                     # = g.arcs[:, 2:] (does not materialise the id columns of a lazy GraphTensor)
         aggregated_arcs = sparse_dense(g.ArcNode, labels)
         n_nodes = g.nodes.shape[0]
         if self.state_vect_dim > 0:

@@ -159,8 +159,9 @@ def csr_from_coo_transposed(coo, *, device=None, with_transpose: bool = False):
 
 
 def csr_build(rows: torch.Tensor, cols: torch.Tensor, vals: torch.Tensor, n_rows: int, n_cols: int, *,
-              with_transpose: bool = False):
-    """ gnn_csr_build on device int32/float32 tensors """
+              with_transpose: bool = False, assume_uniform: bool = False):
+    """ gnn_csr_build on device int32/float32 tensors.  assume_uniform: the caller guarantees that every row holds one
+    repeated value (default ArcNode of the three aggregation modes): no flag is read back, the call does not synchronise """
     from .graph_class import SparseCSR
     l = lib()
     device = rows.device
@@ -175,14 +176,14 @@ def csr_build(rows: torch.Tensor, cols: torch.Tensor, vals: torch.Tensor, n_rows
     ws_bytes = C.c_size_t(0)
     with torch.cuda.device(device):
         args = [_ptr(rows), _ptr(cols), _ptr(vals), nnz, n_rows, n_cols, _ptr(rowptr), _ptr(col_s), _ptr(val_s), _ptr(perm),
-                _ptr(row_scale), _ptr(rowptr_T), _ptr(col_T), _ptr(perm_T), _ptr(val_T), C.byref(uniform)]
+                _ptr(row_scale), _ptr(rowptr_T), _ptr(col_T), _ptr(perm_T), _ptr(val_T), None if assume_uniform else C.byref(uniform)]
         check(l.gnn_csr_build(*args, None, C.byref(ws_bytes), _stream(device)), 'gnn_csr_build(size query)')
         ws = torch.empty(ws_bytes.value, dtype=torch.uint8, device=device)
         check(l.gnn_csr_build(*args, _ptr(ws), C.byref(ws_bytes), _stream(device)), 'gnn_csr_build')
     trim = lambda t, n: None if t is None else t[:n]
     return SparseCSR(rowptr[:n_rows + 1], trim(col_s, nnz), trim(val_s, nnz), trim(perm, nnz), (n_rows, n_cols),
                      rowptr_T=trim(rowptr_T, n_cols + 1), col_T=trim(col_T, nnz), perm_T=trim(perm_T, nnz),
-                     values_T=trim(val_T, nnz), row_scale=row_scale[:n_rows] if uniform.value else None)
+                     values_T=trim(val_T, nnz), row_scale=row_scale[:n_rows] if (assume_uniform or uniform.value) else None)
 
 
 def spmm(rowptr: torch.Tensor, col: torch.Tensor, val: Optional[torch.Tensor], dense: torch.Tensor,

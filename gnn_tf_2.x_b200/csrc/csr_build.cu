@@ -139,7 +139,7 @@ extern "C" int gnn_csr_build(const int32_t* row, const int32_t* col, const float
         return GNN_OK;
     }
     if (*workspace_bytes < need) GNN_FAIL(GNN_ERR_WORKSPACE, "gnn_csr_build: workspace %zu < %zu", *workspace_bytes, need);
-    if (!row || !col || !rowptr || !col_sorted || !val_sorted || !perm || !rows_uniform)
+    if (!row || !col || !rowptr || !col_sorted || !val_sorted || !perm)
         if (nnz > 0 || !rowptr) GNN_FAIL(GNN_ERR_INVALID, "gnn_csr_build: NULL argument");
 
     char* w = (char*)workspace;
@@ -187,6 +187,7 @@ extern "C" int gnn_csr_build(const int32_t* row, const int32_t* col, const float
         GNN_LAUNCH_CHECK();
     }
 
+    if (!rows_uniform) return GNN_OK;   // the caller knows (or does not care): nothing to report, no synchronisation
     int32_t host_flag = 0;
     GNN_CUDA(cudaMemcpyAsync(&host_flag, flag, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
     GNN_CUDA(cudaStreamSynchronize(stream));

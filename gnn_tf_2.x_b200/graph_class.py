@@ -90,6 +90,7 @@ class GraphObject:
 
         self.ArcNode = self.buildArcNode() if ArcNode is None else coo_matrix(ArcNode).astype(self.dtype)
         self.Adjacency = self.buildAdiacency()
+        self._mark_default_structure(ArcNode is None)
 
         # NodeGraph: (graph id, coefficient) per node + optional user-supplied dense matrix
         self._ng_ids: Optional[np.ndarray] = None
@@ -119,6 +120,21 @@ class GraphObject:
                            ArcNode=self.getArcNode(), aggregation_mode=self.aggregation_mode,
                            _endpoints=(self._src.copy(), self._dst.copy()))
 
+    # -----------------------------------------------------------------------------------------------------------------
+    def _structure_refs(self):
+        a, d = self.ArcNode, self.Adjacency
+        return (a, d, a.row, a.col, a.data, d.row, d.col, d.data)
+
+    def _mark_default_structure(self, default: bool) -> None:
+        """ remember that ArcNode / Adjacency are exactly what buildArcNode / buildAdiacency made of the endpoints (and
+        which objects they are): GraphTensor.fromGraphObject then copies the endpoints once instead of four index arrays
+        and knows that the rows of both transposed matrices hold one repeated value """
+        self._struct_refs = self._structure_refs() if default else None
+
+    def has_default_structure(self) -> bool:
+        refs = getattr(self, '_struct_refs', None)
+        return refs is not None and all(x is y for x, y in zip(refs, self._structure_refs()))
+
     def pin_host_buffers(self) -> None:
         """ move the arrays that GraphTensor.fromGraphObject copies to the device into page-locked host memory
         (numpy views over pinned torch storage), so that the host->device copies run at full PCIe/NVLink-C2C speed """
@@ -131,17 +147,26 @@ class GraphObject:
             self._pinned[name] = t
             return t.numpy()
 
+        default = self.has_default_structure()
         self.arcs, self.nodes, self.targets = pin('arcs', self.arcs), pin('nodes', self.nodes), pin('targets', self.targets)
+        self._src32, self._dst32 = pin('src32', self._src.astype(np.int32)), pin('dst32', self._dst.astype(np.int32))
+        self._arc_labels, self._arc_labels_of = pin('arc_labels', self.arcs[:, 2:]), self.arcs   # valid while self.arcs is this array
         for name in ('Adjacency', 'ArcNode'):
             m = getattr(self, name)
             m.row, m.col, m.data = pin(name + '.row', m.row.astype(np.int32)), pin(name + '.col', m.col.astype(np.int32)), \
                 pin(name + '.data', m.data)
+        if default: self._mark_default_structure(True)      # same matrices, new (pinned) arrays
 
     def host_bytes(self) -> int:
         """ bytes GraphTensor.fromGraphObject copies host->device for this graph """
-        total = self.arcs.nbytes + self.nodes.nbytes + self.targets.nbytes + self.set_mask.nbytes + self.output_mask.nbytes
+        total = self.nodes.nbytes + self.targets.nbytes + self.set_mask.nbytes + self.output_mask.nbytes
         total += 4 * self.sample_weights.shape[0]
-        for m in (self.Adjacency, self.ArcNode): total += 4 * (len(m.row) + len(m.col) + len(m.data))
+        # default structure: endpoints once (int32), the two value arrays, arc labels only (the id columns are rebuilt on the device)
+        if self.has_default_structure():
+            total += 4 * (2 * len(self._src) + len(self.Adjacency.data) + len(self.ArcNode.data)) + 4 * self.arcs.shape[0] * (self.arcs.shape[1] - 2)
+        else:
+            total += self.arcs.nbytes
+            for m in (self.Adjacency, self.ArcNode): total += 4 * (len(m.row) + len(m.col) + len(m.data))
         return int(total)
 
     ## STRUCTURE BUILDERS #############################################################################################
@@ -171,6 +196,7 @@ class GraphObject:
         self.aggregation_mode = aggregation_mode
         self.ArcNode = self.buildArcNode()
         self.Adjacency = self.buildAdiacency()
+        self._mark_default_structure(True)
 
     # -----------------------------------------------------------------------------------------------------------------
     def buildNodeGraph(self, problem_based: str):
@@ -417,7 +443,13 @@ class GraphTensor:
         bln = lambda a: torch.as_tensor(np.asarray(a), dtype=torch.bool, device=device) if not isinstance(a, torch.Tensor) \
             else a.to(device=device, dtype=torch.bool)
         self.device = device
-        self.nodes, self.arcs, self.targets = f32(nodes), f32(arcs), f32(targets)
+        self.nodes, self.targets = f32(nodes), f32(targets)
+        # arcs: the full [E, 2 + AL] matrix, or ('endpoints+labels', src, dst, labels) device tensors -- the id columns are
+        # then only materialised when somebody reads .arcs (the loop needs the labels alone)
+        if isinstance(arcs, tuple) and arcs[0] == 'endpoints+labels':
+            self._arcs, self._arc_parts = None, (arcs[1], arcs[2], arcs[3])
+        else:
+            self._arcs, self._arc_parts = f32(arcs), None
         self.sample_weights = f32(sample_weights)
         self.set_mask, self.output_mask = bln(set_mask), bln(output_mask)
         self.aggregation_mode = aggregation_mode
@@ -429,6 +461,23 @@ class GraphTensor:
         self._ng_ids = self._ng_coeff = self._ng_dense = None
         self._ng_cols = 0
         if NodeGraph is not None: self._set_nodegraph(NodeGraph)
+
+    @property
+    def arcs(self):
+        import torch
+        if self._arcs is None:
+            src, dst, labels = self._arc_parts
+            self._arcs = torch.cat([src.to(torch.float32)[:, None], dst.to(torch.float32)[:, None], labels], dim=1)
+        return self._arcs
+
+    @arcs.setter
+    def arcs(self, value):
+        self._arcs, self._arc_parts = value, None
+
+    @property
+    def arc_labels(self):
+        """ arcs[:, 2:] without materialising the id columns """
+        return self._arc_parts[2] if self._arcs is None else self._arcs[:, 2:]
 
     # -----------------------------------------------------------------------------------------------------------------
     def _set_nodegraph(self, value):
@@ -537,8 +586,29 @@ class GraphTensor:
     def fromGraphObject(cls, g: GraphObject, *, device=None):
         """ GraphObject -> GraphTensor; both sparse matrices are transposed and row-major ordered on the GPU
         (graph_class.py:354-361). """
-        adjacency = cls.COO2SparseTransposedTensor(g.Adjacency, device=device, with_transpose=True)
-        arcnode = cls.COO2SparseTransposedTensor(g.ArcNode, device=device, with_transpose=False)
+        if g.has_default_structure():
+            # ArcNode / Adjacency as built from the endpoints: Adjacency^T = (row dst, col src), ArcNode^T = (row dst, col arc id).
+            # The endpoints travel once (int32), the arc ids are generated on the device, and both builds skip the
+            # uniformity read-back (rows of both matrices hold one repeated value in all three aggregation modes), so they
+            # run on the GPU while the host goes on copying
+            import torch
+            from . import _native
+            dev = _native.default_device() if device is None else torch.device(device)
+            n_nodes, n_arcs = g.nodes.shape[0], g.arcs.shape[0]
+            as_dev = lambda a, dt: torch.as_tensor(np.ascontiguousarray(a, dtype=dt), device=dev)
+            dst = as_dev(getattr(g, '_dst32', g._dst), np.int32)
+            src = as_dev(getattr(g, '_src32', g._src), np.int32)
+            adjacency = _native.csr_build(dst, src, as_dev(g.Adjacency.data, np.float32), n_nodes, n_nodes, with_transpose=True,
+                                          assume_uniform=True)
+            arcnode = _native.csr_build(dst, torch.arange(n_arcs, dtype=torch.int32, device=dev), as_dev(g.ArcNode.data, np.float32),
+                                        n_nodes, n_arcs, with_transpose=False, assume_uniform=True)
+            labels = g._arc_labels if getattr(g, '_arc_labels_of', None) is g.arcs else g.arcs[:, 2:]
+            return cls(nodes=g.nodes, arcs=('endpoints+labels', src, dst, as_dev(labels, np.float32)), targets=g.targets, set_mask=g.set_mask,
+                       output_mask=g.output_mask, sample_weights=g.sample_weights, NodeGraph=g._nodegraph_payload(), Adjacency=adjacency,
+                       ArcNode=arcnode, aggregation_mode=g.aggregation_mode, device=device)
+        else:
+            adjacency = cls.COO2SparseTransposedTensor(g.Adjacency, device=device, with_transpose=True)
+            arcnode = cls.COO2SparseTransposedTensor(g.ArcNode, device=device, with_transpose=False)
         return cls(nodes=g.nodes, arcs=g.arcs, targets=g.targets, set_mask=g.set_mask, output_mask=g.output_mask,
                    sample_weights=g.sample_weights, NodeGraph=g._nodegraph_payload(), Adjacency=adjacency,
                    ArcNode=arcnode, aggregation_mode=g.aggregation_mode, device=device)

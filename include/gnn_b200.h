@@ -61,7 +61,8 @@ int gnn_device_info(int32_t* sm_count, int32_t* smem_optin_bytes, int32_t* cc_ma
  * Optional transposed structure (pass NULL rowptr_T to skip): entries sorted by (col, CSR position):
  *   rowptr_T[n_cols+1], col_T[nnz] (= row of the entry), perm_T[nnz] (= CSR position), val_T[nnz].
  * Call with workspace == NULL to get the required size in *workspace_bytes.
- * Synchronises the stream once (to report rows_uniform to the host).
+ * Synchronises the stream once (to report rows_uniform to the host); pass rows_uniform == NULL to skip the report and
+ * the synchronisation (e.g. for the default ArcNode of the three aggregation modes, whose rows are uniform by construction).
  */
 int gnn_csr_build(const int32_t* row, const int32_t* col, const float* val, /* device [nnz] */
                   int64_t nnz, int64_t n_rows, int64_t n_cols,

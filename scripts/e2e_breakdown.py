@@ -31,21 +31,21 @@ for rep in range(4):
     names = ['x0 h2d', 'fromGraphObject (h2d + csr build)', 'Loop', 'd2h']
     print(rep, ' | '.join(f'{n} {1e3 * (b - a):.2f} ms' for n, a, b in zip(names, t[:-1], t[1:])), f'| total {1e3 * (t[-1] - t[0]):.2f} ms', flush=True)
 
-# inside fromGraphObject
+# inside fromGraphObject (default structure path)
 from gnn_b200 import _native
-for rep in range(2):
+print('default structure:', g_host.has_default_structure(), 'host bytes', g_host.host_bytes())
+for rep in range(3):
     t0 = time.perf_counter()
-    coo = g_host.Adjacency
-    rows = torch.as_tensor(np.ascontiguousarray(coo.col, dtype=np.int32), device=device)
-    cols = torch.as_tensor(np.ascontiguousarray(coo.row, dtype=np.int32), device=device)
-    vals = torch.as_tensor(np.ascontiguousarray(coo.data, dtype=np.float32), device=device)
+    as_dev = lambda a, dt: torch.as_tensor(np.ascontiguousarray(a, dtype=dt), device=device)
+    dst = as_dev(g_host._dst32, np.int32); src = as_dev(g_host._src32, np.int32); val = as_dev(g_host.Adjacency.data, np.float32)
     sync(); t1 = time.perf_counter()
-    csr = _native.csr_build(rows, cols, vals, int(coo.shape[1]), int(coo.shape[0]), with_transpose=True)
-    sync(); t2 = time.perf_counter()
-    an = GraphTensor.COO2SparseTransposedTensor(g_host.ArcNode, device=device, with_transpose=False)
+    csr = _native.csr_build(dst, src, val, 1_000_000, 1_000_000, with_transpose=True, assume_uniform=True)
+    t1b = time.perf_counter(); sync(); t2 = time.perf_counter()
+    val2 = as_dev(g_host.ArcNode.data, np.float32)
+    an = _native.csr_build(dst, torch.arange(10_000_000, dtype=torch.int32, device=device), val2, 1_000_000, 10_000_000, assume_uniform=True)
     sync(); t3 = time.perf_counter()
     gt = GraphTensor(nodes=g_host.nodes, arcs=g_host.arcs, targets=g_host.targets, set_mask=g_host.set_mask, output_mask=g_host.output_mask,
                      sample_weights=g_host.sample_weights, NodeGraph=g_host._nodegraph_payload(), Adjacency=csr, ArcNode=an,
                      aggregation_mode=g_host.aggregation_mode, device=device)
     sync(); t4 = time.perf_counter()
-    print(f'adjacency h2d {1e3*(t1-t0):.2f} | adjacency csr_build(+T) {1e3*(t2-t1):.2f} | arcnode h2d+build {1e3*(t3-t2):.2f} | dense tensors h2d {1e3*(t4-t3):.2f} ms', flush=True)
+    print(f'endpoints+val h2d {1e3*(t1-t0):.2f} | adjacency csr_build(+T) enqueue {1e3*(t1b-t1):.2f} total {1e3*(t2-t1):.2f} | arcnode h2d+build {1e3*(t3-t2):.2f} | dense tensors h2d {1e3*(t4-t3):.2f} ms', flush=True)
