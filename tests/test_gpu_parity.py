@@ -92,6 +92,33 @@ def test_row_scale_detection():
         np.testing.assert_allclose(gt.Adjacency.row_scale.cpu().numpy(), want.astype(np.float32), rtol=1e-7)
 
 
+def test_default_structure_upload_equals_generic_path():
+    """ GraphTensor.fromGraphObject of a default-built graph (endpoints once, arc ids on the device, no read-back) must give
+    bit-identical structures and the same arcs matrix as the generic COO path; pinned host buffers change nothing """
+    _require_gpu()
+    from gnn_b200.graph_class import GraphObject, GraphTensor
+    c = random_case(seed=6, n_nodes=500, n_arcs=4000, AL=2)
+    for mode in ('average', 'normalized', 'sum'):
+        g = GraphObject(c['arcs'], c['nodes'], c['targets'], set_mask=c['set_mask'], output_mask=c['output_mask'], aggregation_mode=mode)
+        assert g.has_default_structure()
+        fast = GraphTensor.fromGraphObject(g)
+        g.pin_host_buffers()
+        assert g.has_default_structure()
+        pinned = GraphTensor.fromGraphObject(g)
+        g._struct_refs = None                               # force the generic path
+        assert not g.has_default_structure()
+        slow = GraphTensor.fromGraphObject(g)
+        for gt in (fast, pinned):
+            for name in ('Adjacency', 'ArcNode'):
+                a, b = getattr(gt, name), getattr(slow, name)
+                for field in ('rowptr', 'col', 'values', 'perm', 'row_scale', 'rowptr_T', 'col_T', 'perm_T'):
+                    x, y = getattr(a, field), getattr(b, field)
+                    assert (x is None) == (y is None), (name, field)
+                    if x is not None: assert torch.equal(x, y), (name, field)
+            assert torch.equal(gt.arc_labels, slow.arcs[:, 2:])
+            assert torch.equal(gt.arcs, slow.arcs)
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # forward (inference) parity
 # ---------------------------------------------------------------------------------------------------------------------

@@ -115,6 +115,26 @@ def test_oracle_structures_match_reference(golden_dir):
                                    rtol=1e-6, atol=1e-6)
 
 
+def test_default_structure_flag():
+    """ the fast upload path of GraphTensor.fromGraphObject is only taken for matrices the builders made themselves """
+    rng = np.random.default_rng(0)
+    arcs = np.concatenate([rng.integers(0, 20, (60, 2)).astype(float), rng.random((60, 1))], axis=1)
+    nodes, targets = rng.random((20, 3)), rng.random((20, 2))
+    g = GraphObject(arcs, nodes, targets)
+    assert g.has_default_structure()
+    g.setAggregation('sum')
+    assert g.has_default_structure()
+    custom = GraphObject(arcs, nodes, targets, ArcNode=g.getArcNode())
+    assert not custom.has_default_structure()
+    g.ArcNode = g.ArcNode.copy()                       # replaced by the user: no assumption survives
+    assert not g.has_default_structure()
+    g.setAggregation('average')
+    assert g.has_default_structure()
+    g.Adjacency.data = g.Adjacency.data * 2            # a new array object
+    assert not g.has_default_structure()
+    assert g.host_bytes() > 0
+
+
 def test_error_behaviour():
     nodes, arcs, targs = np.zeros((3, 2)), np.array([[0, 1, 1.], [1, 2, 1.]]), np.zeros((3, 2))
     with pytest.raises(ValueError): GraphObject(arcs, nodes, targs, aggregation_mode='max')
