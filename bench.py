@@ -324,8 +324,14 @@ def main():
             r2 = dist_graph.bench_partitioned(g2, wl2, build_gnn, args, device, rank, world, with_e2e=False)
             variant = {'workload': other + (': sources within +-2048 of the destination (boundary rows travel)' if other == 'c4l' else ': uniform sources'),
                        'value': r2['value'], 'ms_per_step': r2['ms_per_step'], 'iterations': r2['iterations'], 'partition': r2['partition']}
+        batches = None
+        if not args.skip_variant:
+            r5 = bench_graph_batches(args, device, rank, world)
+            batches = {'workload': r5['config']['workload'], 'scaling': 'weak', 'value': r5['value'], 'unit': 'arc-updates/s (forward+backward+Adam)',
+                       'ms_per_step': r5['ms_per_step'], 'arcs_per_rank': r5['config']['arcs_per_rank']}
         if rank == 0:
             result['source_distribution_variant'] = variant
+            result['graph_batches'] = batches
             config['partition'] = result.pop('partition')
             result.update({'metric': metric, 'unit': 'arc-updates/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(3, args.warmup),
                            'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
@@ -447,6 +453,13 @@ def main():
                    'ms_per_launch': ms_k2 / max(n2, 1), 'roofline_frac': alg_bytes / (ms_k2 / max(n2, 1) * 1e-3) / 1e9 / peak_gbs}
         del gt2, g2
 
+    # --- sharded graph batches (C5, weak scaling: the same per-rank work at every N), training steps -----------------
+    batches = None
+    if not args.skip_variant:
+        r5 = bench_graph_batches(args, device, rank, world)
+        batches = {'workload': r5['config']['workload'], 'scaling': 'weak', 'value': r5['value'], 'unit': 'arc-updates/s (forward+backward+Adam)',
+                   'ms_per_step': r5['ms_per_step'], 'arcs_per_rank': r5['config']['arcs_per_rank']}
+
     # --- CPU baseline: oracle port on the host cores, bounded sample ----------------------------------------------
     cpu = None
     if not args.skip_cpu:
@@ -458,7 +471,7 @@ def main():
     print(json.dumps({'metric': metric, 'value': value, 'unit': 'arc-updates/s', 'n_gpus': 1, 'steps': args.steps, 'warmup': max(3, args.warmup),
                       'ms_per_step': ms_fwd, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32',
                       'data': 'synthetic', 'config': config, 'iterations': k_fwd, 'e2e': e2e, 'gpu_launches': int(launches_fwd),
-                      'roofline': roofline, 'train': train, 'source_distribution_variant': variant, 'cpu_baseline': cpu,
+                      'roofline': roofline, 'train': train, 'source_distribution_variant': variant, 'graph_batches': batches, 'cpu_baseline': cpu,
                       'clocks': clocks.summary()}))
 
 
