@@ -377,7 +377,25 @@ static __global__ void state_bwd_scatter_kernel(const int* __restrict__ k_ptr, i
     const int lig = (int)(item % LPN);
     if (u >= N) return;
     const int e0 = __ldg(rowptr_T + u), e1 = __ldg(rowptr_T + u + 1);
-    float4 acc = gather_rows<DP, HAS_VAL, false>(GA, 4 * lig, e0, e1, col_T, val_T);
+    // batches of 8 arcs: all indices, then all 8 row loads back to back (nothing with a scoreboard in between), then the sum in
+    // stored order; past the end the last arc is repeated (its row is loaded, not summed) so that the batch stays branch-free
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int e = e0; e < e1; e += 8) {
+        int idx[8];
+        float w[8];
+        float4 r[8];
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            const int ee = min(e + b, e1 - 1);
+            idx[b] = __ldg(col_T + ee);
+            if (HAS_VAL) w[b] = __ldg(val_T + ee);
+        }
+#pragma unroll
+        for (int b = 0; b < 8; ++b) r[b] = ldg4(GA + (size_t)idx[b] * DP + 4 * lig);
+#pragma unroll
+        for (int b = 0; b < 8; ++b)
+            if (e + b < e1) acc = HAS_VAL ? fma4(w[b], r[b], acc) : add4(acc, r[b]);
+    }
     const float4 gs = ldg4(GS + (size_t)u * DP + 4 * lig);
     st4(G + (size_t)u * DP + 4 * lig, add4(acc, gs));
 }
