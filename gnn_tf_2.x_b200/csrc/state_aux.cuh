@@ -107,12 +107,20 @@ static __global__ void bn_stats_kernel(const int* __restrict__ go_cur, const dou
                                 float* __restrict__ moving_mean, float* __restrict__ moving_var, float eps, float momentum,
                                 float* __restrict__ stats /* [4][DP]: mean, var, a, c */) {
     if (*reinterpret_cast<const volatile int*>(go_cur) == 0) return;
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= DP) return;
+    // one CTA of 64 threads per column: strided partial sums, then a fixed shuffle / shared-memory tree (deterministic)
+    const int j = blockIdx.x;
+    double s1 = 0., s2 = 0.;
+    if (j < D)
+        for (int b = threadIdx.x; b < nblocks; b += blockDim.x) { s1 += partial[(size_t)b * 2 * DP + j]; s2 += partial[(size_t)b * 2 * DP + DP + j]; }
+    for (int off = 16; off > 0; off >>= 1) { s1 += __shfl_down_sync(0xffffffffu, s1, off); s2 += __shfl_down_sync(0xffffffffu, s2, off); }
+    __shared__ double red[2][2];
+    if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5][0] = s1; red[threadIdx.x >> 5][1] = s2; }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    s1 = red[0][0] + red[1][0];
+    s2 = red[0][1] + red[1][1];
     float mean = 0.f, var = 0.f, a = 0.f, c = 0.f;
     if (j < D) {
-        double s1 = 0., s2 = 0.;
-        for (int b = 0; b < nblocks; ++b) { s1 += partial[(size_t)b * 2 * DP + j]; s2 += partial[(size_t)b * 2 * DP + DP + j]; }
         const double m = s1 / (double)N;
         double v = s2 / (double)N - m * m;
         if (v < 0.) v = 0.;

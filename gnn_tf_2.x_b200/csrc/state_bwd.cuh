@@ -442,14 +442,21 @@ static __global__ void bn_bwd_reduce_kernel(const int* __restrict__ k_ptr, int t
 }
 
 // sums -> means used by the node kernel; dgamma += sum(G*xhat), dbeta += sum(G) (accumulated over iterations)
+// one CTA of 64 threads per column: strided partial sums, then a fixed shuffle / shared-memory tree (deterministic)
 static __global__ void bn_bwd_finalize_kernel(const int* __restrict__ k_ptr, int t, const double* __restrict__ partial, int nblocks, int DP,
                                        int D, long long N, float* __restrict__ sums, double* __restrict__ dgamma_dbeta) {
     if (t >= *reinterpret_cast<const volatile int*>(k_ptr)) return;
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= DP) return;
+    const int j = blockIdx.x;
     double s1 = 0., s2 = 0.;
     if (j < D)
-        for (int b = 0; b < nblocks; ++b) { s1 += partial[(size_t)b * 2 * DP + j]; s2 += partial[(size_t)b * 2 * DP + DP + j]; }
+        for (int b = threadIdx.x; b < nblocks; b += blockDim.x) { s1 += partial[(size_t)b * 2 * DP + j]; s2 += partial[(size_t)b * 2 * DP + DP + j]; }
+    for (int off = 16; off > 0; off >>= 1) { s1 += __shfl_down_sync(0xffffffffu, s1, off); s2 += __shfl_down_sync(0xffffffffu, s2, off); }
+    __shared__ double red[2][2];
+    if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5][0] = s1; red[threadIdx.x >> 5][1] = s2; }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    s1 = red[0][0] + red[1][0];
+    s2 = red[0][1] + red[1][1];
     sums[j] = (float)(s1 / (double)N);
     sums[DP + j] = (float)(s2 / (double)N);
     dgamma_dbeta[j] += s2;

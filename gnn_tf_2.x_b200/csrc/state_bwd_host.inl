@@ -104,7 +104,7 @@ extern "C" int gnn_state_loop_backward(const gnn_graph* g, const gnn_mlp* net, c
             const float* stats = w.stats + (size_t)t * 4 * lay.DP;
             bn_reduce<<<red_grid, 256, 0, stream>>>(kptr, t, w.G, p.y_t, stats, net->bn_eps, N, w.bn_bwd_partial);
             GNN_LAUNCH_CHECK();
-            bn_bwd_finalize_kernel<<<(lay.DP + 31) / 32, 32, 0, stream>>>(kptr, t, w.bn_bwd_partial, red_grid, lay.DP, lay.D, N,
+            bn_bwd_finalize_kernel<<<lay.DP, 64, 0, stream>>>(kptr, t, w.bn_bwd_partial, red_grid, lay.DP, lay.D, N,
                                                                          w.bn_bwd_sums, w.bn_dgdb);
             GNN_LAUNCH_CHECK();
             p.bn_stats = stats;

@@ -365,7 +365,7 @@ extern "C" int gnn_state_loop_forward(const gnn_graph* g, const gnn_mlp* net, co
                         p.go_next ? (int64_t)((char*)p.go_next - (char*)workspace) : (int64_t)-1);
         if (bn_train) {
             float* stats = w.stats + (size_t)t * 4 * lay.DP;
-            bn_stats_kernel<<<(lay.DP + 31) / 32, 32, 0, stream>>>(go + t, w.bn_partial, plan.grid, lay.DP, lay.D, N, net->bn_gamma,
+            bn_stats_kernel<<<lay.DP, 64, 0, stream>>>(go + t, w.bn_partial, plan.grid, lay.DP, lay.D, N, net->bn_gamma,
                                                                   net->bn_beta, net->bn_moving_mean, net->bn_moving_var, net->bn_eps,
                                                                   net->bn_momentum, stats);
             GNN_LAUNCH_CHECK();
