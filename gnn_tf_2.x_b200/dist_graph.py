@@ -139,6 +139,12 @@ class GraphPartition:
         self.nodes = f32(g.nodes)                                 # replicated (label widths are small)
         self.n_arcs_local = n_mine
         self.halo = HaloPlan(self.Adjacency.col, self.bounds, rank, world, group) if world > 1 else None
+        import os
+        env = os.environ.get('GNN_B200_FUSED')                    # '0' / '1': force the NCCL / the fused exchange (experiments)
+        if env is not None: fused = env != '0'
+        # measured on 8 x B200 with every row travelling to every peer (uniform sources): NCCL all-gather 14.5 ms per 50 iterations,
+        # fused 16-byte peer stores 16.1 ms (at 2 GPUs the fused path wins 1.6x); boundary-only exchanges stay fused
+        if env is None and self.halo is not None and self.halo.use_allgather and world >= 8: fused = False
         self.fused = bool(fused and world > 1 and world <= 8 and self.device.type == 'cuda')
         self._ws = self._handle = self._peer_mask = self._state_offsets = None
         self._order = torch.zeros(1, dtype=torch.int32, device=self.device) if world > 1 else None
