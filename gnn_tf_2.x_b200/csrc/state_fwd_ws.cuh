@@ -32,14 +32,11 @@
 
 namespace gnn {
 
+// named barriers (0 is __syncthreads): the issue warps once per tile, the MLP warps once at the end of the kernel
 #define GNN_BAR_ISSUE 1
-#define GNN_BAR_MLP0 2    // +group
-#define GNN_BAR_FULL0 4   // +b
-#define GNN_BAR_EMPTY0 6  // +b
-#define GNN_BAR_MLP_ALL 8
+#define GNN_BAR_MLP_ALL 2
 
 __device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
-__device__ __forceinline__ void named_bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
     const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(dst), "l"(gmem_src));
