@@ -88,7 +88,7 @@ static_assert(4 * WS_MLP_GROUPS * (WS_REGS_MLP - WS_REGS_LAUNCH) <= 8 * (WS_REGS
               "setmaxnreg.inc only draws on what this CTA's own warps released (spare registers of the SM do not count)");
 constexpr int WS_SLOTS = 16;       // sub-tiles in flight at most (mbarrier slots of the ring)
 constexpr int WS_ROWQ = 8;         // row-pointer / scale buffers (tiles)
-constexpr int WS_COLPAD = 256;     // slack behind each arc-source buffer: the batched index loads may run past the last arc
+constexpr int WS_COLPAD = 384;     // slack behind each arc-source buffer: the batched index loads may run past the last arc
 
 #ifndef GNN_WS_SLEEP_MLP
 #define GNN_WS_SLEEP_MLP 256
@@ -313,19 +313,24 @@ __global__ void __launch_bounds__(WS_THREADS, 1) state_iter_ws_kernel(const Iter
                 // every landed source row -> ring (asynchronous, no registers): one row per lane group and step
                 float* lb = land0 + (size_t)start * DP + 4 * lig;
                 const int* sc = scol + a0;
-                // 8 independent index loads, then 8 copies (all but the first predicated).  Index loads past the sub-tile's last
-                // arc stay inside the padded buffer and their values are not used.
-                static_assert(7 * NGRP < WS_COLPAD, "index loads run at most 7 NGRP entries past the last arc");
-                if (!(p.ws_debug & 1))
-                for (int r = grp; r < cnt; r += 8 * NGRP) {
-                    const int* si = sc + r;
-                    float* di = lb + (size_t)r * DP;
-                    int sidx[8];
+                // Index loads past the sub-tile's last arc stay inside the padded buffer and their values are not used.
+                static_assert(11 * NGRP < WS_COLPAD, "index loads run at most 11 NGRP entries past the last arc");
+                auto copy_batch = [&](auto width_c) {      // WIDTH independent index loads, then WIDTH copies (all but the first predicated)
+                    constexpr int WIDTH = decltype(width_c)::value;
+                    for (int r = grp; r < cnt; r += WIDTH * NGRP) {
+                        const int* si = sc + r;
+                        float* di = lb + (size_t)r * DP;
+                        int sidx[WIDTH];
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) sidx[k] = si[k * NGRP];
-                    cp_async16(di, xl + (size_t)sidx[0] * DP);
+                        for (int k = 0; k < WIDTH; ++k) sidx[k] = si[k * NGRP];
+                        cp_async16(di, xl + (size_t)sidx[0] * DP);
 #pragma unroll
-                    for (int k = 1; k < 8; ++k) cp_async16_if(r + k * NGRP < cnt, di + k * NGRP * DP, xl + (size_t)sidx[k] * DP);
+                        for (int k = 1; k < WIDTH; ++k) cp_async16_if(r + k * NGRP < cnt, di + k * NGRP * DP, xl + (size_t)sidx[k] * DP);
+                    }
+                };
+                if (!(p.ws_debug & 1)) {
+                    if (cnt > 4 * NGRP) copy_batch(std::integral_constant<int, 12>{});   // dense sub-tiles: one or two passes
+                    else copy_batch(std::integral_constant<int, 4>{});                   // sparse sub-tiles: no wasted slots
                 }
                 cp_async_mbar_arrive_u32(landed_u32 + 8 * slot);
                 slot += 2;
