@@ -90,6 +90,9 @@ constexpr int WS_SLOTS = 16;       // sub-tiles in flight at most (mbarrier slot
 constexpr int WS_ROWQ = 8;         // row-pointer / scale buffers (tiles)
 constexpr int WS_COLPAD = 384;     // slack behind each arc-source buffer: the batched index loads may run past the last arc
 
+#ifndef GNN_WS_CONS_UNROLL
+#define GNN_WS_CONS_UNROLL 4
+#endif
 #ifndef GNN_WS_SLEEP_MLP
 #define GNN_WS_SLEEP_MLP 256
 #endif
@@ -375,7 +378,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) state_iter_ws_kernel(const Iter
                 float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
                 int r = r0;
                 const int rl = min(r1, a0 + cnt);
-#pragma unroll 4
+                constexpr int CONS_UNROLL = GNN_WS_CONS_UNROLL;
+#pragma unroll CONS_UNROLL
                 for (; r < rl; ++r) {
                     const float4 v = ld4(lb + (ptrdiff_t)r * DP);
                     if (HAS_VAL) acc = fma4(sv[r], v, acc);
