@@ -82,8 +82,8 @@ constexpr int WS_CONS = 256;       // consume threads (warps 8-15): group g (4 w
 constexpr int WS_ISSUE = 256;      // issue threads (warps 16-23): two groups of 4 warps, even / odd sub-tiles
 constexpr int WS_ISSUE_GRP = 128;
 constexpr int WS_THREADS = 768;
-// registers per thread after the roles split (setmaxnreg): 768 x 80 at launch -> MLP 104, consume 64, issue 48
-constexpr int WS_REGS_LAUNCH = 80, WS_REGS_MLP = 104, WS_REGS_CONS = 64, WS_REGS_ISSUE = 48;
+// registers per thread after the roles split (setmaxnreg): 768 x 80 at launch -> MLP 128, consume 64, issue 48
+constexpr int WS_REGS_LAUNCH = 80, WS_REGS_MLP = 128, WS_REGS_CONS = 64, WS_REGS_ISSUE = 48;
 static_assert(4 * WS_MLP_GROUPS * (WS_REGS_MLP - WS_REGS_LAUNCH) <= 8 * (WS_REGS_LAUNCH - WS_REGS_ISSUE) + 8 * (WS_REGS_LAUNCH - WS_REGS_CONS),
               "setmaxnreg.inc only draws on what this CTA's own warps released (spare registers of the SM do not count)");
 constexpr int WS_SLOTS = 16;       // sub-tiles in flight at most (mbarrier slots of the ring)
@@ -418,14 +418,12 @@ __global__ void __launch_bounds__(WS_THREADS, 1) state_iter_ws_kernel(const Iter
         const float* tb = tile0 + (size_t)mgroup * TN * SAG + (size_t)(16 * mwarp + fg) * SAG + 4 * ft;   // my row fg of the tile, + 8 SAG: row fg + 8
         double* bn_mine = &bn_acc[tid >> 5][0][0];   // [2][DP], private to this warp
 
-        int round = 0;
-        for (long long tile = first + (long long)mgroup * stride; tile < ntiles; tile += WS_MLP_GROUPS * stride, ++round) {
+        // own state rows fg, fg + 8 (columns 16 q + 4 ft .. + 3) and constant rows (columns 8 s + 2 ft, + 1; CS <= 2) of a tile,
+        // loaded ONE TILE OF THIS GROUP AHEAD (a whole tile period in flight)
+        float4 xnext[2][NQ];
+        float2 cnext[2][2];
+        auto load_own = [&](long long tile) {
             const long long n0 = tile * TN;
-            const int nvalid = (int)min((long long)TN, p.N - n0);
-            // own state rows fg, fg + 8 (columns 16 q + 4 ft .. + 3) and constant rows (columns 8 s + 2 ft, + 1; CS <= 2):
-            // in flight while this warp waits for the aggregates and multiplies them
-            float4 xcur[2][NQ];
-            float2 ccur[2][2];
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const long long n = n0 + 16 * mwarp + fg + 8 * h;
@@ -433,11 +431,27 @@ __global__ void __launch_bounds__(WS_THREADS, 1) state_iter_ws_kernel(const Iter
                 const float* xr = p.x_in + (size_t)(p.row_offset + n) * DP + 4 * ft;
                 const float* cr = p.cst + (size_t)n * CP + 2 * ft;
 #pragma unroll
-                for (int q = 0; q < NQ; ++q) xcur[h][q] = valid ? ldg4(xr + 16 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int q = 0; q < NQ; ++q) xnext[h][q] = valid ? ldg4(xr + 16 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                 for (int s2 = 0; s2 < 2; ++s2)
-                    ccur[h][s2] = (valid && 8 * s2 + 2 * ft < CP) ? __ldg(reinterpret_cast<const float2*>(cr + 8 * s2)) : make_float2(0.f, 0.f);
+                    cnext[h][s2] = (valid && 8 * s2 + 2 * ft < CP) ? __ldg(reinterpret_cast<const float2*>(cr + 8 * s2)) : make_float2(0.f, 0.f);
             }
+        };
+        if (first + (long long)mgroup * stride < ntiles) load_own(first + (long long)mgroup * stride);
+
+        int round = 0;
+        for (long long tile = first + (long long)mgroup * stride; tile < ntiles; tile += WS_MLP_GROUPS * stride, ++round) {
+            const long long n0 = tile * TN;
+            const int nvalid = (int)min((long long)TN, p.N - n0);
+            float4 xcur[2][NQ];
+            float2 ccur[2][2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) xcur[h][q] = xnext[h][q];
+                ccur[h][0] = cnext[h][0]; ccur[h][1] = cnext[h][1];
+            }
+            if (tile + WS_MLP_GROUPS * stride < ntiles) load_own(tile + WS_MLP_GROUPS * stride);
 
             // Dense layer on the tensor cores: 16 x DP outputs per warp, 3 x TF32 (fp32-accurate)
             float acc[NT8][4];
