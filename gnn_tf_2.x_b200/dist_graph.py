@@ -134,7 +134,8 @@ class GraphPartition:
         self.Adjacency = _native.csr_build(dst_loc, src_all.index_select(0, mine), vals, self.n_local, self.n_global)
         self.ArcNode = _native.csr_build(dst_loc, torch.arange(n_mine, dtype=torch.int32, device=dev),
                                          up(an.data, torch.float32).index_select(0, mine), self.n_local, max(n_mine, 1))
-        self.arc_labels = up(g.arcs[:, 2:], torch.float32).index_select(0, mine)
+        labels = g._arc_labels if getattr(g, '_arc_labels_of', None) is g.arcs else g.arcs[:, 2:]     # page-locked copy when pinned
+        self.arc_labels = up(labels, torch.float32).index_select(0, mine)
         f32 = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.float32), device=dev)
         self.nodes = f32(g.nodes)                                 # replicated (label widths are small)
         self.n_arcs_local = n_mine
