@@ -223,6 +223,69 @@ def cpu_port_run(wl, iterations: int, repeats: int = 1):
     return wl['E'] * k / best, best, threads
 
 
+
+# ---------------------------------------------------------------------------------------------------------------------
+# parity of the TIMED configuration against the CPU oracle (the checker leg; never inside a timed region)
+# ---------------------------------------------------------------------------------------------------------------------
+def _tensor_errors(got, want):
+    """ (max-norm relative error of the tensor, 99th percentile and maximum of the ELEMENT-WISE relative error
+    |got - want| / (|want| + 1e-3 max|want|): the floor keeps elements near zero from dividing by nothing) """
+    got, want = np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64)
+    scale = float(np.max(np.abs(want))) if want.size else 0.0
+    diff = np.abs(got - want)
+    elem = diff / (np.abs(want) + 1e-3 * scale + 1e-30)
+    return float(diff.max() / (scale + 1e-6)), float(np.percentile(elem, 99)), float(elem.max())
+
+
+def parity_check(wl, gnn, gt, device, iterations: int, training: bool, tol: float = 1e-4):
+    """ `iterations` iterations of the loop on the full-size workload through the GPU path and through the oracle port:
+    iteration count exact, state / outputs (and, training=True, loss + BPTT gradients + moving statistics) within tol.
+    :return: dict for the JSON line; 'ok' False makes bench.py refuse to print a value """
+    import torch
+    from oracle import gnn_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    g = O.OracleGraph.build(wl['arcs'], wl['nodes'], wl['targets'], 'n', None, None, 1, None, 'average', endpoints=(wl['src'], wl['dst']))
+    net_s = O.OracleMLP.from_weights(wl['ws'], ['selu'], batchnorm=True, requires_grad=training)
+    net_o = O.OracleMLP.from_weights(wl['wo'], ['softmax'], batchnorm=False, requires_grad=training)
+    x0 = torch.from_numpy(wl['x0'])
+    kw = dict(state_vect_dim=wl['DS'], max_iteration=iterations, threshold=0.0, x0=x0, fast_spmm=True)
+    saved_iter, saved_w = gnn.max_iteration, [w.copy() for w in gnn.net_state.get_weights()]
+    gnn.max_iteration = iterations
+    tensors = {}
+    try:
+        if not training:
+            with torch.no_grad():
+                k_ref, state_ref, out_ref = O.loop(g, net_s, net_o, **kw)
+                k, state, out = gnn.Loop(gt, training=False)
+            tensors = {'state': (state.cpu().numpy(), state_ref.numpy()), 'out': (out.cpu().numpy(), out_ref.numpy())}
+        else:
+            k_ref, loss_ref, gs_ref, go_ref, out_ref, state_ref = O.training_gradients(g, net_s, net_o, O.categorical_crossentropy, mean=True, **kw)
+            targs = gnn.get_filtered_tensor(gt, gt.targets)
+            weights = gnn.get_filtered_tensor(gt, gt.sample_weights)
+            k, state, out = gnn.Loop(gt, training=True)
+            loss = (gnn.loss_function(targs, out, **gnn.loss_args) * weights).sum()
+            ws, wo = gnn.net_state.trainable_variables, gnn.net_output.trainable_variables
+            grads = torch.autograd.grad(loss, ws + wo, allow_unused=True)
+            grads = [torch.zeros_like(v) if gr is None else gr for v, gr in zip(ws + wo, grads)]
+            tensors = {'state': (state.detach().cpu().numpy(), state_ref.numpy()), 'out': (out.detach().cpu().numpy(), out_ref.numpy()),
+                       'loss': (np.array([float(loss)]), np.array([float(loss_ref)]))}
+            for i, (gr, ref) in enumerate(zip(grads[:len(ws)], gs_ref)): tensors[f'grad_state[{i}]'] = ((gr / k).cpu().numpy(), ref.numpy())
+            for i, (gr, ref) in enumerate(zip(grads[len(ws):], go_ref)): tensors[f'grad_output[{i}]'] = (gr.cpu().numpy(), ref.numpy())
+            bn = gnn.net_state.layers[-1]
+            tensors['moving_mean'] = (bn.moving_mean.cpu().numpy(), net_s.moving_mean.numpy())
+            tensors['moving_var'] = (bn.moving_variance.cpu().numpy(), net_s.moving_var.numpy())
+    finally:
+        gnn.max_iteration = saved_iter
+        gnn.net_state.set_weights(saved_w)          # the training-mode loop moved the BatchNormalization statistics
+        torch.set_num_threads(1)
+    errs = {name: _tensor_errors(a, b) for name, (a, b) in tensors.items()}
+    worst = max(errs, key=lambda n: errs[n][0])
+    k_equal = float(k) == float(k_ref)
+    return {'ok': bool(k_equal and errs[worst][0] <= tol), 'k_equal': k_equal, 'k': float(k), 'tol': tol, 'iterations': iterations,
+            'training': training, 'max_rel': errs[worst][0], 'worst_tensor': worst,
+            'elementwise_rel_p99': max(e[1] for e in errs.values()), 'elementwise_rel_max': max(e[2] for e in errs.values()),
+            'per_tensor_max_rel': {n: e[0] for n, e in errs.items()}, 'kernel': None}
+
 # ---------------------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -239,6 +302,8 @@ def main():
     ap.add_argument('--cpu-iterations', type=int, default=40, help='iterations of the workload timed on the CPU port')
     ap.add_argument('--skip-train', action='store_true')
     ap.add_argument('--skip-cpu', action='store_true')
+    ap.add_argument('--skip-parity', action='store_true', help='skip the oracle check of the timed configuration (3 iterations on the full graph)')
+    ap.add_argument('--parity-iterations', type=int, default=3)
     ap.add_argument('--skip-variant', action='store_true', help='skip the side-by-side forward run on the other source distribution')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
@@ -355,6 +420,15 @@ def main():
         torch.cuda.synchronize()
         return start.elapsed_time(stop) / steps
 
+    # --- parity of the timed configuration: same graph, same nets, same kernel plan, `parity-iterations` iterations ------
+    parity = None
+    if not args.skip_parity:
+        parity = {args.workload: parity_check(wl, gnn, gt, device, args.parity_iterations, training=False)}
+        parity[args.workload]['kernel'] = _native.last_forward_kernel()
+        if not args.skip_train:
+            parity[args.workload + '_train'] = parity_check(wl, gnn, gt, device, args.parity_iterations, training=True)
+            parity[args.workload + '_train']['kernel'] = _native.last_forward_kernel()
+
     # --- value: forward loop, inputs resident ---------------------------------------------------------------------
     ks = []
 
@@ -436,6 +510,12 @@ def main():
                          _endpoints=(wl2['src'], wl2['dst']))
         gt2 = GraphTensor.fromGraphObject(g2, device=device)
         gnn.initial_state = torch.as_tensor(wl2['x0'], device=device)
+        if parity is not None:
+            parity[other] = parity_check(wl2, gnn, gt2, device, args.parity_iterations, training=False)
+            parity[other]['kernel'] = _native.last_forward_kernel()
+            if not args.skip_train:
+                parity[other + '_train'] = parity_check(wl2, gnn, gt2, device, args.parity_iterations, training=True)
+                parity[other + '_train']['kernel'] = _native.last_forward_kernel()
         ks2 = []
 
         def fwd2():
@@ -468,7 +548,12 @@ def main():
                'sample': f'{args.cpu_iterations} iterations of the forward loop on the full {args.workload} graph ({sec:.2f} s)',
                'note': 'torch-CPU restatement of the reference TF2 path (oracle/), not TensorFlow'}
 
-    print(json.dumps({'metric': metric, 'value': value, 'unit': 'arc-updates/s', 'n_gpus': 1, 'steps': args.steps, 'warmup': max(3, args.warmup),
+    if parity is not None:
+        failed = {name: p for name, p in parity.items() if not p['ok']}
+        if failed:     # a fast kernel whose results differ from the reference's is not done: no value is printed
+            print(json.dumps({'metric': metric, 'value': None, 'error': 'parity check of the timed configuration failed', 'parity': failed}))
+            raise SystemExit(2)
+    print(json.dumps({'metric': metric, 'parity': parity, 'value': value, 'unit': 'arc-updates/s', 'n_gpus': 1, 'steps': args.steps, 'warmup': max(3, args.warmup),
                       'ms_per_step': ms_fwd, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32',
                       'data': 'synthetic', 'config': config, 'iterations': k_fwd, 'e2e': e2e, 'gpu_launches': int(launches_fwd),
                       'roofline': roofline, 'train': train, 'source_distribution_variant': variant, 'graph_batches': batches, 'cpu_baseline': cpu,

@@ -34,16 +34,9 @@ extern "C" int gnn_state_loop_backward(const gnn_graph* g, const gnn_mlp* net, c
         return GNN_OK;
     }
 
-    // re-pack: the forward of a training step may have been followed by nothing that changes the weights, but the
-    // affine slot differs between training / inference BatchNormalization, so pack again (cheap)
-    {
-        PackParams pp;
-        pp.net = *net; pp.lay = lay; pp.wpack = w.wpack; pp.state_loop = 1;
-        pp.bn_inference = lay.has_bn && !a->training;
-        pack_net_kernel<<<(lay.total_floats + 255) / 256, 256, 0, stream>>>(pp);
-        GNN_LAUNCH_CHECK();
-    }
-
+    // The packed net in the workspace (weights, transposed copies, final affine) is the one the forward call packed: it IS the
+    // value saved for backward.  Not re-packed from the live parameter pointers: an in-place update of the parameters between
+    // forward and backward (an optimizer step of an interleaved user loop) must not mix new weights with the saved iterates.
     // kernel + shared memory plan of the node kernel
     BwdNodeParams p;
     memset(&p, 0, sizeof(p));

@@ -24,7 +24,9 @@ struct IterParams {
     const int32_t* rowptr;
     const int32_t* col;
     const float* val;        // NULL => row scale in cst[:, C]
+    const float* row_scale;  // [N] the same scale as a contiguous array (bulk-copied per tile by the warp-specialised kernel)
     long long N;
+    long long E;             // entries of col / val
     long long row_offset;    // global id of local row 0 (node-range partition; 0 on a single GPU)
     int n_peers, rank;       // fused NVLink exchange: new rows are also stored into the peers' state buffers
     float* peer_out[GNN_MAX_PEERS];

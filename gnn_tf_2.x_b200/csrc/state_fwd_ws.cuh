@@ -3,17 +3,20 @@
 // Why: the gather of a uniform-random graph is bound by how many 128-byte rows an SM keeps in flight.  A gather-only
 // microbenchmark on B200 (scripts/gather_microbench.cu) needs >= 1000 rows in flight per SM to reach the L2/HBM limit;
 // the symmetric kernel (state_fwd.cuh) holds its rows in registers and cannot have that many in flight next to the MLP.
-// Here the rows land in shared memory through cp.async (no registers, deep queue) and THREE roles run concurrently in
-// one persistent CTA of 768 threads per SM (register budgets re-split per role with setmaxnreg).  Work unit of the
+// Here the rows land in shared memory through cp.async (no registers, deep queue) and FOUR roles run concurrently in
+// one persistent CTA of 768 threads per SM (21 working warps) (register budgets re-split per role with setmaxnreg).  Work unit of the
 // gather: a SUB-TILE of 16 nodes (= one m16 mma block); 4 sub-tiles = one 64-node tile.  The landing zone is a ring of
 // 8 or 16 slots, one sub-tile each: a slot is in flight from the moment its copies are issued until its segment sums are
 // done (a ring of two whole-tile stages spends half of its life waiting to be consumed).
 //
-//   issue warps   (8): two groups of 4 (even / odd sub-tiles); never wait for data.  Per tile: arc sources / row pointers
-//                      of tile j+2 -> shared memory (cp.async, completion -> mbarrier COLS); per sub-tile: wait for its
-//                      slot (mbarrier FREE), one 16-byte cp.async per lane for every source row; completion of all of
-//                      them arrives on the slot's mbarrier LANDED (cp.async.mbarrier.arrive.noinc).  They block only on
-//                      the LSU queue: the memory pipe is fed continuously.
+//   loader warp   (1): stages what the other roles index with, two tiles ahead, with BULK ASYNC COPIES (cp.async.bulk,
+//                      one elected thread, no per-element instructions): the arc sources of a tile (mbarrier COLS) and its
+//                      row pointers / per-node scales / per-arc weights (mbarrier ROWS).  A CTA owns a CONTIGUOUS range of
+//                      tiles, so every copy is one aligned contiguous block.
+//   issue warps   (4): warp w lands sub-tile w of every tile; never waits for data.  Per sub-tile: wait for its slot
+//                      (mbarrier FREE), then per 4 source rows ONE index load from shared memory, ONE address multiply-add
+//                      and ONE 16-byte cp.async per lane; completion of all of them arrives on the slot's mbarrier LANDED
+//                      (cp.async.mbarrier.arrive.noinc).  ~1 warp instruction per landed row (round 1: ~5).
 //   consume warps (8): two groups of 4 (even / odd tiles); warp c owns sub-tile c.  wait LANDED -> segment sums out of
 //                      shared memory in stored order (deterministic, no atomics, packed add.f32x2) into rows 16c..16c+15
 //                      of aggregate tile g -> mbarrier FULL[g][c] for MLP warp c of group g, mbarrier FREE for the slot
@@ -32,8 +35,7 @@
 
 namespace gnn {
 
-// named barriers (0 is __syncthreads): the issue warps once per tile, the MLP warps once at the end of the kernel
-#define GNN_BAR_ISSUE 1
+// named barriers (0 is __syncthreads): the MLP warps once at the end of the kernel
 #define GNN_BAR_MLP_ALL 2
 
 __device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
@@ -79,25 +81,31 @@ constexpr int WS_MLP = 128;        // threads of ONE MLP group (4 warps)
 constexpr int WS_MLP_GROUPS = 2;   // group g takes the tiles it = g, g+2, ... (tile buffer g)
 constexpr int WS_MLP_ALL = WS_MLP * WS_MLP_GROUPS;   // warps 0-7
 constexpr int WS_CONS = 256;       // consume threads (warps 8-15): group g (4 warps) takes the tiles it = g, g+2, ...; warp c sub-tile c
-constexpr int WS_ISSUE = 256;      // issue threads (warps 16-23): two groups of 4 warps, even / odd sub-tiles
-constexpr int WS_ISSUE_GRP = 128;
-constexpr int WS_THREADS = 768;
-// registers per thread after the roles split (setmaxnreg): 768 x 80 at launch -> MLP 128, consume 64, issue 48
-constexpr int WS_REGS_LAUNCH = 80, WS_REGS_MLP = 128, WS_REGS_CONS = 64, WS_REGS_ISSUE = 48;
-static_assert(4 * WS_MLP_GROUPS * (WS_REGS_MLP - WS_REGS_LAUNCH) <= 8 * (WS_REGS_LAUNCH - WS_REGS_ISSUE) + 8 * (WS_REGS_LAUNCH - WS_REGS_CONS),
+constexpr int WS_ISSUE = 128;      // issue threads (warps 16-19): warp w lands sub-tile w of every tile
+constexpr int WS_LOADER = 32;      // loader warp (warp 20): bulk copies of arc sources / row pointers / scales
+constexpr int WS_IDLE = 96;        // warps 21-23 give their registers back and exit: the register file is split over the 4 SM
+                                   // sub-partitions (16K each), so 21 warps get no more registers per thread at launch than 24 do
+constexpr int WS_THREADS = WS_MLP_ALL + WS_CONS + WS_ISSUE + WS_LOADER + WS_IDLE;   // 768
+// registers per thread after the roles split (setmaxnreg): 768 x 80 at launch -> MLP 128, consume 64, issue 48, loader 40, idle 24.
+// Per sub-partition: 2 MLP + 2 consume + 1 issue + 1 loader / idle warp = 2*128 + 2*64 + 48 + 40 = 472 <= 512 registers per lane.
+constexpr int WS_REGS_LAUNCH = 80, WS_REGS_MLP = 128, WS_REGS_CONS = 64, WS_REGS_ISSUE = 48, WS_REGS_LOADER = 40, WS_REGS_IDLE = 24;
+static_assert(WS_THREADS * WS_REGS_LAUNCH <= 65536, "registers of one SM at launch");
+static_assert(WS_MLP_ALL * (WS_REGS_MLP - WS_REGS_LAUNCH) <= WS_ISSUE * (WS_REGS_LAUNCH - WS_REGS_ISSUE) + WS_CONS * (WS_REGS_LAUNCH - WS_REGS_CONS) +
+                                                                  WS_LOADER * (WS_REGS_LAUNCH - WS_REGS_LOADER) + WS_IDLE * (WS_REGS_LAUNCH - WS_REGS_IDLE),
               "setmaxnreg.inc only draws on what this CTA's own warps released (spare registers of the SM do not count)");
 constexpr int WS_SLOTS = 16;       // sub-tiles in flight at most (mbarrier slots of the ring)
-constexpr int WS_ROWQ = 8;         // row-pointer / scale buffers (tiles)
-constexpr int WS_COLPAD = 384;     // slack behind each arc-source buffer: the batched index loads may run past the last arc
+constexpr int WS_ROWQ = 8;         // row-pointer / scale buffers (tiles): staged 2 tiles ahead of the issue, consumed <= 4 tiles behind it
+constexpr int WS_COLQ = 4;         // arc-source buffers (tiles): staged up to 3 tiles ahead of the issue
+constexpr int WS_COLPAD = 8;       // slack of each arc-source / weight buffer: the copy starts at the 16-byte boundary below the first arc
 
 #ifndef GNN_WS_CONS_UNROLL
 #define GNN_WS_CONS_UNROLL 4
 #endif
 #ifndef GNN_WS_SLEEP_MLP
-#define GNN_WS_SLEEP_MLP 256
+#define GNN_WS_SLEEP_MLP 64
 #endif
 #ifndef GNN_WS_SLEEP_CONS
-#define GNN_WS_SLEEP_CONS 96
+#define GNN_WS_SLEEP_CONS 32
 #endif
 // mbarrier (shared memory, CTA scope)
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
@@ -146,24 +154,34 @@ static inline size_t ws_weight_floats(const NetLayout& lay) { return (size_t)ws_
 // shared-memory footprint (bytes): `ring` landing rows (slots x rows per slot), arc-index capacity `capc` per tile
 static inline size_t ws_smem_bytes(const NetLayout& lay, int ring, int capc, bool has_val) {
     size_t fl = ws_weight_floats(lay) + WS_MLP_GROUPS * (size_t)WS_TN * ws_tile_stride(lay.DP) + (size_t)ring * lay.DP + WS_ROWQ * 68 + WS_ROWQ * WS_TN +
-                3 * (size_t)(capc + WS_COLPAD) + (has_val ? WS_ROWQ * (size_t)capc : 0);   // tiles x2, ring, row pointers / scales, arc indices x3, weights
+                WS_COLQ * (size_t)(capc + WS_COLPAD) + (has_val ? WS_ROWQ * (size_t)(capc + WS_COLPAD) : 0);   // weights, tiles x2, ring, row pointers / scales, arc sources, arc weights
     return fl * 4;
+}
+
+// bulk asynchronous copy global -> shared (UBLKCP): one thread, one instruction, any multiple of 16 bytes; both addresses
+// 16-byte aligned.  Completion is counted in bytes on the mbarrier (expect_tx).
+__device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gmem_src, int bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, int bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 
 template <int DP, bool HAS_VAL>
 __global__ void __launch_bounds__(WS_THREADS, 1) state_iter_ws_kernel(const IterParams p) {
     constexpr int TN = WS_TN, LPN = DP / 4;
-    constexpr int GPW = 32 / LPN;            // lane groups per warp
-    constexpr int NGRP = WS_ISSUE_GRP / LPN; // lane groups of one issue group
+    constexpr int GPW = 32 / LPN;            // lane groups per warp = source rows per warp-wide cp.async
     constexpr int NPG = WS_SUB / GPW;        // nodes per lane group of a consume warp
     static_assert(GPW * NPG == WS_SUB, "lane mapping");
     static_assert(DP % 8 == 0 && TN == 64 && WS_NSUB == 4, "4 MLP warps x 16 nodes, DP / 8 accumulator fragments each");
+    static_assert(WS_ISSUE == 32 * WS_NSUB, "one issue warp per sub-tile of a tile");
 
     if (*reinterpret_cast<const volatile int*>(p.go_cur) == 0) return;
 
     const NetLayout& net = p.net;
     const int tid = threadIdx.x;
-    const int CP = net.CP, capc = p.scol_cap;
+    const int CP = net.CP, capc = p.scol_cap, capb = capc + WS_COLPAD;
     const int nslot = p.ring_slots, slotcap = p.slot_rows;   // landing ring: nslot slots of slotcap rows, sub-tile j -> slot j % nslot
 
     extern __shared__ __align__(16) float smem[];
@@ -178,10 +196,11 @@ __global__ void __launch_bounds__(WS_THREADS, 1) state_iter_ws_kernel(const Iter
     float* land0 = tile0 + WS_MLP_GROUPS * TN * SAG;    // [nslot][slotcap][DP]
     int* srow0 = reinterpret_cast<int*>(land0 + (size_t)nslot * slotcap * DP);   // [WS_ROWQ][68]
     float* sscale0 = reinterpret_cast<float*>(srow0 + WS_ROWQ * 68);     // [WS_ROWQ][TN]
-    int* scol0 = reinterpret_cast<int*>(sscale0 + WS_ROWQ * TN);         // [3][capc]
-    float* sval0 = reinterpret_cast<float*>(scol0 + 3 * (capc + WS_COLPAD));           // [WS_ROWQ][capc] (HAS_VAL; read by the consume warps)
+    int* scol0 = reinterpret_cast<int*>(sscale0 + WS_ROWQ * TN);         // [WS_COLQ][capb]
+    float* sval0 = reinterpret_cast<float*>(scol0 + WS_COLQ * capb);     // [WS_ROWQ][capb] (HAS_VAL; read by the consume warps)
     __shared__ int s_flag;
-    __shared__ __align__(8) uint64_t bar_landed[WS_SLOTS], bar_free[WS_SLOTS], bar_cols[3], bar_full[WS_MLP_GROUPS][WS_NSUB], bar_empty[WS_MLP_GROUPS][WS_NSUB];
+    __shared__ __align__(8) uint64_t bar_landed[WS_SLOTS], bar_free[WS_SLOTS], bar_cols[WS_COLQ], bar_colfree[WS_COLQ], bar_rows[WS_ROWQ], bar_rowfree[WS_ROWQ],
+        bar_full[WS_MLP_GROUPS][WS_NSUB], bar_empty[WS_MLP_GROUPS][WS_NSUB];
     __shared__ double bn_acc[4 * WS_MLP_GROUPS][2][DP];   // BatchNormalization batch statistics, one private row per MLP warp
 
     // The mma K and N indices are ours to permute as long as A, B and C agree.  Both are laid out so that a lane's fragment
@@ -217,15 +236,18 @@ __global__ void __launch_bounds__(WS_THREADS, 1) state_iter_ws_kernel(const Iter
     for (int i = tid; i < 4 * WS_MLP_GROUPS * 2 * DP; i += WS_THREADS) (&bn_acc[0][0][0])[i] = 0.;
     if (tid == 0) {
         s_flag = 0;
-        for (int i = 0; i < WS_SLOTS; ++i) { mbar_init(&bar_landed[i], WS_ISSUE_GRP); mbar_init(&bar_free[i], 32); }
-        for (int i = 0; i < 3; ++i) mbar_init(&bar_cols[i], WS_ISSUE);
-        for (int i = 0; i < WS_MLP_GROUPS * WS_NSUB; ++i) { mbar_init(&bar_full[0][0] + i, 32); mbar_init(&bar_empty[0][0] + i, 32); }
+        for (int i = 0; i < WS_SLOTS; ++i) { mbar_init(&bar_landed[i], 32); mbar_init(&bar_free[i], 1); }     // LANDED: every lane of the slot's issue warp; FREE: its consume warp
+        for (int i = 0; i < WS_COLQ; ++i) { mbar_init(&bar_cols[i], 1); mbar_init(&bar_colfree[i], WS_NSUB); }   // COLS: the loader (+ bytes); COLFREE: the 4 issue warps
+        for (int i = 0; i < WS_ROWQ; ++i) { mbar_init(&bar_rows[i], 1); mbar_init(&bar_rowfree[i], 2 * WS_NSUB); }   // ROWFREE: 4 issue + 4 consume warps
+        for (int i = 0; i < WS_MLP_GROUPS * WS_NSUB; ++i) { mbar_init(&bar_full[0][0] + i, 1); mbar_init(&bar_empty[0][0] + i, 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");     // visible to the async proxy (bulk copies)
     }
     __syncthreads();
 
+    // this CTA's tiles: a CONTIGUOUS range (its row pointers, arc sources and weights are contiguous in memory)
     const long long ntiles = (p.N + TN - 1) / TN;
-    const long long first = blockIdx.x, stride = gridDim.x;
-    auto tile_at = [&](int seq) { return first + (long long)seq * stride; };
+    const long long t0 = ntiles * blockIdx.x / gridDim.x;
+    const int ntl = (int)(ntiles * (blockIdx.x + 1) / gridDim.x - t0);
 
     // sub-tile c of a tile lands the arcs [a0, a0 + cnt) (tile-relative) in its ring slot; arcs beyond the slot (or beyond
     // the staged arc indices) are read directly by the consume warp
@@ -236,110 +258,104 @@ __global__ void __launch_bounds__(WS_THREADS, 1) state_iter_ws_kernel(const Iter
         cnt = max(0, min(a1 - a0, slotcap));
     };
 
-    if (tid >= WS_MLP_ALL + WS_CONS) {
+    if (tid >= WS_MLP_ALL + WS_CONS + WS_ISSUE + WS_LOADER) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(WS_REGS_IDLE));   // idle warps: registers back to the pool, done
+    } else if (tid >= WS_MLP_ALL + WS_CONS + WS_ISSUE) {
+        // ============================================ LOADER WARP ==============================================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(WS_REGS_LOADER));
+        const int lane = tid & 31;
+        const long long E = p.E;
+        // arc range of every tile = rowptr at the tile boundaries: 32 boundaries per load (one per lane), fetched one batch ahead,
+        // so that no global-load latency sits between two tiles of the staging loop
+        auto fetch_bounds = [&](int base) {
+            return base + lane <= ntl ? __ldg(p.rowptr + min((t0 + base + lane) * TN, p.N)) : 0;
+        };
+        int bcur = fetch_bounds(0), bnext = fetch_bounds(32);
+        for (int s = 0; s < ntl; ++s) {
+            const long long n0 = (t0 + s) * TN;
+            const int q8 = s & (WS_ROWQ - 1), q3 = s % WS_COLQ;
+            if ((s & 31) == 0 && s > 0) { bcur = bnext; bnext = fetch_bounds(s + 32); }
+            const int e0 = __shfl_sync(0xffffffffu, bcur, s & 31);
+            const int e1 = (s & 31) == 31 ? __shfl_sync(0xffffffffu, bnext, 0) : __shfl_sync(0xffffffffu, bcur, (s + 1) & 31);   // (warp-uniform)
+            const int e0a = e0 & ~3;                                            // 16-byte boundary at or below the first arc
+            const int narc = min(e1 - e0a, capb - 4), narc4 = (narc + 3) & ~3;  // staged entries (a multiple of 16 bytes)
+            const bool arcs_safe = (long long)e0a + narc4 <= E;                 // the rounded-up copy stays inside the array
+            const bool rows_safe = n0 + 68 <= p.N + 1 && n0 + TN <= p.N;
+            // ---- row pointers, per-node scales (or per-arc weights): buffer q8, free once tile s - WS_ROWQ has been consumed
+            if (s >= WS_ROWQ) mbar_wait<64>(&bar_rowfree[q8], ((s / WS_ROWQ) - 1) & 1);
+            int* srow = srow0 + q8 * 68;
+            float* ssc = sscale0 + q8 * TN;
+            float* sv = sval0 + (size_t)q8 * capb;
+            if (rows_safe && (!HAS_VAL || arcs_safe)) {
+                if (lane == 0) {
+                    mbar_expect_tx(&bar_rows[q8], 68 * 4 + (HAS_VAL ? narc4 * 4 : TN * 4));
+                    bulk_copy_g2s(srow, p.rowptr + n0, 68 * 4, &bar_rows[q8]);
+                    if (HAS_VAL) { if (narc4 > 0) bulk_copy_g2s(sv, p.val + e0a, narc4 * 4, &bar_rows[q8]); }
+                    else bulk_copy_g2s(ssc, p.row_scale + n0, TN * 4, &bar_rows[q8]);
+                }
+            } else {   // last tile of the graph: element-wise, nothing is read past the end of an array
+                for (int i = lane; i <= TN; i += 32) srow[i] = __ldg(p.rowptr + min(n0 + i, p.N));
+                if (HAS_VAL) { for (int i = lane; i < narc; i += 32) sv[i] = __ldg(p.val + e0a + i); }
+                else for (int i = lane; i < TN; i += 32) ssc[i] = n0 + i < p.N ? __ldg(p.row_scale + n0 + i) : 0.f;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_rows[q8]);
+            }
+            // ---- arc sources: buffer q3, free once the issue warps are done with tile s - WS_COLQ
+            if (s >= WS_COLQ) mbar_wait<64>(&bar_colfree[q3], ((s / WS_COLQ) - 1) & 1);
+            int* sc = scol0 + (size_t)q3 * capb;
+            if (arcs_safe) {
+                if (lane == 0) {
+                    mbar_expect_tx(&bar_cols[q3], narc4 * 4);
+                    if (narc4 > 0) bulk_copy_g2s(sc, p.col + e0a, narc4 * 4, &bar_cols[q3]);
+                }
+            } else {
+                for (int i = lane; i < narc; i += 32) sc[i] = __ldg(p.col + e0a + i);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_cols[q3]);
+            }
+        }
+    } else if (tid >= WS_MLP_ALL + WS_CONS) {
         // ============================================ ISSUE WARPS ==============================================
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(WS_REGS_ISSUE));
-        const int gt = tid - WS_MLP_ALL - WS_CONS;
-        const int ig = gt / WS_ISSUE_GRP;                       // issue group: sub-tiles ig, ig + 2 of every tile
-        const int grp = (gt % WS_ISSUE_GRP) / LPN, lig = gt % LPN;
-
-        // arc sources (+ weights), row pointers (+ per-node scales) of tile seq: asynchronous 4-byte copies.  The arc range
-        // [e0, e1) comes from registers (read one iteration earlier straight from global memory).
-        auto request_cols = [&](long long tile, int seq, int e0, int e1) {
-            const long long n0 = tile * TN;
-            const int q8 = seq & (WS_ROWQ - 1), q3 = seq % 3;
-            const int ecount = min(e1 - e0, capc);
-            for (int r = gt; r < ecount; r += WS_ISSUE) {
-                cp_async4(scol0 + (size_t)q3 * (capc + WS_COLPAD) + r, p.col + e0 + r);
-                if (HAS_VAL) cp_async4(sval0 + (size_t)q8 * capc + r, p.val + e0 + r);
-            }
-            for (int i = gt; i <= TN; i += WS_ISSUE) cp_async4(srow0 + q8 * 68 + i, p.rowptr + min(n0 + i, p.N));
-            if (!HAS_VAL)
-                for (int i = gt; i < TN; i += WS_ISSUE) {
-                    if (n0 + i < p.N) cp_async4(sscale0 + q8 * TN + i, p.cst + (size_t)(n0 + i) * CP + net.C);
-                    else sscale0[q8 * TN + i] = 0.f;
-                }
-        };
-        auto tile_arcs = [&](long long tile, int& e0, int& e1) {
-            e0 = __ldg(p.rowptr + tile * TN);
-            e1 = __ldg(p.rowptr + min(tile * TN + TN, p.N));
-        };
-
-        // nslot is even: slot j % nslot has the parity of the sub-tile, i.e. a slot is only ever used by ONE issue group,
-        // which is therefore the only thread set waiting on its FREE barrier (never more than one phase behind)
-        int slot = ig, m = 0;                   // slot (= j % nslot) of this group's next sub-tile; sub-tiles issued so far
+        const int c = (tid - WS_MLP_ALL - WS_CONS) >> 5;        // my sub-tile of every tile
+        const int lane = tid & 31, grp = lane / LPN, lig = lane % LPN;
         const unsigned landed_u32 = smem_u32(bar_landed), free_u32 = smem_u32(bar_free);
-        int wphase = 0;                         // FREE phase to wait for; flips each time `slot` wraps
-        const int per_round = nslot / 2;        // this group's slots
-
-        int e0, e1;
-        for (int sq = 0; sq < 2; ++sq)
-            if (tile_at(sq) < ntiles) {
-                tile_arcs(tile_at(sq), e0, e1);
-                request_cols(tile_at(sq), sq, e0, e1);
-                cp_async_mbar_arrive(&bar_cols[sq]);
-            }
-        if (tile_at(2) < ntiles) tile_arcs(tile_at(2), e0, e1);     // arc range of tile it + 2, one iteration ahead
-        int it = 0;
-        for (long long tile = first; tile < ntiles; tile += stride, ++it) {
-            const long long t2 = tile + 2 * stride, t3 = tile + 3 * stride;
-            // Buffers request_cols is about to overwrite hold the row pointers / scales / weights of tile it+2-WS_ROWQ = it-6.
-            // A sub-tile x of that tile shares its slot with y = x + nslot, a sub-tile of a tile <= it-2 (nslot <= 16);
-            // y has been issued (everybody is past tile it-1), and y is only issued after x has been consumed.
-            named_bar_sync(GNN_BAR_ISSUE, WS_ISSUE);                 // every issue thread is done reading the indices of tile it-1
-            if (t2 < ntiles) {
-                request_cols(t2, it + 2, e0, e1);
-                cp_async_mbar_arrive(&bar_cols[(it + 2) % 3]);
-            }
-            if (t3 < ntiles) tile_arcs(t3, e0, e1);
-            mbar_wait(&bar_cols[it % 3], (it / 3) & 1);              // indices / row pointers of tile it have landed
-            const int* srow = srow0 + (it & (WS_ROWQ - 1)) * 68;
-            const int* scol = scol0 + (size_t)(it % 3) * (capc + WS_COLPAD);
-            const float* xl = p.x_in + 4 * lig;
-            // arc ranges of this group's two sub-tiles (c = ig, ig + 2): five independent loads, one latency
-            int a0s[2], cnts[2];
-            {
-                const int eb = srow[0];
+        const float* xl = p.x_in + 4 * lig;
+        const int slot_shift = nslot == 8 ? 3 : 4;
+        for (int s = 0; s < ntl; ++s) {
+            const int q8 = s & (WS_ROWQ - 1), q3 = s % WS_COLQ;
+            mbar_wait(&bar_rows[q8], (s / WS_ROWQ) & 1);           // row pointers of tile s
+            mbar_wait(&bar_cols[q3], (s / WS_COLQ) & 1);           // arc sources of tile s
+            const int* srow = srow0 + q8 * 68;
+            const int eb = srow[0];
+            const int a0 = srow[WS_SUB * c] - eb;
+            const int cnt = max(0, min(min(srow[WS_SUB * c + WS_SUB] - eb, capc) - a0, slotcap));
+            const int j = WS_NSUB * s + c, slot = j & (nslot - 1);
+            // a slot is only ever used by ONE issue warp and ONE consume warp (nslot is a multiple of 4): nobody waits on
+            // its barriers more than one phase behind
+            if (j >= nslot) mbar_wait_u32(free_u32 + 8 * slot, ((j >> slot_shift) - 1) & 1);   // the slot's previous sub-tile has been consumed
+            // every source row -> ring (asynchronous, no registers): one row per lane group and step
+            const int* si = scol0 + (size_t)q3 * capb + (eb & 3) + a0;
+            const unsigned lb = smem_u32(land0 + (size_t)slot * slotcap * DP + 4 * lig);
+            if (!(p.ws_debug & 1)) {
+                // batches of 8 steps: 8 independent index loads, 8 address multiply-adds, 8 copies (no dependent pair back to back)
+                int r = grp;
+                for (; r + 7 * GPW < cnt; r += 8 * GPW) {
+                    int src[8];
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int c = ig + 2 * h;
-                    const int lo = srow[WS_SUB * c] - eb, hi = min(srow[WS_SUB * c + WS_SUB] - eb, capc);
-                    a0s[h] = lo;
-                    cnts[h] = max(0, min(hi - lo, slotcap));
+                    for (int k = 0; k < 8; ++k) src[k] = si[r + k * GPW];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(lb + (unsigned)(r + k * GPW) * (DP * 4)), "l"(xl + (size_t)src[k] * DP));
+                }
+                for (; r < cnt; r += GPW) {
+                    const int src = si[r];
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(lb + (unsigned)r * (DP * 4)), "l"(xl + (size_t)src * DP));
                 }
             }
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int a0 = a0s[h], cnt = cnts[h];
-                if (m >= per_round) mbar_wait_u32(free_u32 + 8 * slot, wphase);   // the slot's previous sub-tile has been consumed
-                const int start = slot * slotcap;
-                // every landed source row -> ring (asynchronous, no registers): one row per lane group and step
-                float* lb = land0 + (size_t)start * DP + 4 * lig;
-                const int* sc = scol + a0;
-                // Index loads past the sub-tile's last arc stay inside the padded buffer and their values are not used.
-                static_assert(11 * NGRP < WS_COLPAD, "index loads run at most 11 NGRP entries past the last arc");
-                auto copy_batch = [&](auto width_c) {      // WIDTH independent index loads, then WIDTH copies (all but the first predicated)
-                    constexpr int WIDTH = decltype(width_c)::value;
-                    for (int r = grp; r < cnt; r += WIDTH * NGRP) {
-                        const int* si = sc + r;
-                        float* di = lb + (size_t)r * DP;
-                        int sidx[WIDTH];
-#pragma unroll
-                        for (int k = 0; k < WIDTH; ++k) sidx[k] = si[k * NGRP];
-                        cp_async16(di, xl + (size_t)sidx[0] * DP);
-#pragma unroll
-                        for (int k = 1; k < WIDTH; ++k) cp_async16_if(r + k * NGRP < cnt, di + k * NGRP * DP, xl + (size_t)sidx[k] * DP);
-                    }
-                };
-                if (!(p.ws_debug & 1)) {
-                    if (cnt > 4 * NGRP) copy_batch(std::integral_constant<int, 12>{});   // dense sub-tiles: one or two passes
-                    else copy_batch(std::integral_constant<int, 4>{});                   // sparse sub-tiles: no wasted slots
-                }
-                cp_async_mbar_arrive_u32(landed_u32 + 8 * slot);
-                slot += 2;
-                ++m;
-                if (slot >= nslot) { slot -= nslot; if (m > per_round) wphase ^= 1; }
-            }
+            cp_async_mbar_arrive_u32(landed_u32 + 8 * slot);
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(&bar_colfree[q3]); mbar_arrive(&bar_rowfree[q8]); }
         }
         cp_async_wait_group<0>();
     } else if (tid >= WS_MLP_ALL) {
@@ -354,21 +370,22 @@ __global__ void __launch_bounds__(WS_THREADS, 1) state_iter_ws_kernel(const Iter
         const int b = cg;
         const int slot_shift = nslot == 8 ? 3 : 4;
         int round = 0;                                      // it / 2
-        for (int it = cg; tile_at(it) < ntiles; it += 2, ++round) {
-            const long long tile = tile_at(it);
+        for (int it = cg; it < ntl; it += 2, ++round) {
+            const long long tile = t0 + it;
             const int j = WS_NSUB * it + cw, slot = j & (nslot - 1), phase = (j >> slot_shift) & 1;
             const int q8 = it & (WS_ROWQ - 1);
             const long long n0 = tile * TN;
             const int nvalid = (int)min((long long)TN, p.N - n0);
             const int* srow = srow0 + q8 * 68;
-            mbar_wait<GNN_WS_SLEEP_CONS>(&bar_landed[slot], phase);            // rows of the sub-tile, row pointers (and weights) of the tile
+            mbar_wait<GNN_WS_SLEEP_CONS>(&bar_rows[q8], (it / WS_ROWQ) & 1);   // row pointers / scales (/ weights) of the tile (bulk copies)
+            mbar_wait<GNN_WS_SLEEP_CONS>(&bar_landed[slot], phase);            // rows of the sub-tile
             int a0, cnt;
             sub_range(srow, cw, a0, cnt);
             const int start = slot * slotcap;
             if (round > 0) mbar_wait<GNN_WS_SLEEP_CONS>(&bar_empty[b][cw], (round - 1) & 1);   // MLP warp cw of group b is done with tile it - WS_MLP_GROUPS
             const int ebase = srow[0];
             const float* lb = land0 + ((size_t)start - a0) * DP + 4 * lig;   // row of tile-relative arc r: lb + r * DP
-            const float* sv = sval0 + (size_t)q8 * capc;
+            const float* sv = sval0 + (size_t)q8 * capb + (ebase & 3);       // weight of tile-relative arc r (staged from the 16-byte boundary below)
             float* tb = tile0 + (size_t)b * TN * SAG + 4 * lig;
             // segment sums of this lane group's NPG nodes out of the ring, stored order
 #pragma unroll 1
@@ -398,8 +415,12 @@ __global__ void __launch_bounds__(WS_THREADS, 1) state_iter_ws_kernel(const Iter
                 if (p.agg_save && i < nvalid) st4_hint(p.agg_save + (size_t)(n0 + i) * DP + 4 * lig, acc, stream_pol);
                 st4(tb + i * SAG, acc);
             }
-            mbar_arrive(&bar_free[slot]);
-            mbar_arrive(&bar_full[b][cw]);
+            __syncwarp();                                  // every lane's reads of the slot / row buffers and writes of the tile rows are done
+            if (lane == 0) {
+                mbar_arrive(&bar_free[slot]);
+                mbar_arrive(&bar_rowfree[q8]);
+                mbar_arrive(&bar_full[b][cw]);
+            }
         }
     } else {
         // ============================================= MLP WARPS ==============================================
@@ -437,10 +458,11 @@ __global__ void __launch_bounds__(WS_THREADS, 1) state_iter_ws_kernel(const Iter
                     cnext[h][s2] = (valid && 8 * s2 + 2 * ft < CP) ? __ldg(reinterpret_cast<const float2*>(cr + 8 * s2)) : make_float2(0.f, 0.f);
             }
         };
-        if (first + (long long)mgroup * stride < ntiles) load_own(first + (long long)mgroup * stride);
+        if (mgroup < ntl) load_own(t0 + mgroup);
 
         int round = 0;
-        for (long long tile = first + (long long)mgroup * stride; tile < ntiles; tile += WS_MLP_GROUPS * stride, ++round) {
+        for (int it = mgroup; it < ntl; it += WS_MLP_GROUPS, ++round) {
+            const long long tile = t0 + it;
             const long long n0 = tile * TN;
             const int nvalid = (int)min((long long)TN, p.N - n0);
             float4 xcur[2][NQ];
@@ -451,7 +473,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) state_iter_ws_kernel(const Iter
                 for (int q = 0; q < NQ; ++q) xcur[h][q] = xnext[h][q];
                 ccur[h][0] = cnext[h][0]; ccur[h][1] = cnext[h][1];
             }
-            if (tile + WS_MLP_GROUPS * stride < ntiles) load_own(tile + WS_MLP_GROUPS * stride);
+            if (it + WS_MLP_GROUPS < ntl) load_own(tile + WS_MLP_GROUPS);
 
             // Dense layer on the tensor cores: 16 x DP outputs per warp, 3 x TF32 (fp32-accurate)
             float acc[NT8][4];
@@ -479,7 +501,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) state_iter_ws_kernel(const Iter
                 mma_step(2 * NQ + CS + 2 * q, g0.x, g1.x, g0.y, g1.y);
                 mma_step(2 * NQ + CS + 2 * q + 1, g0.z, g1.z, g0.w, g1.w);
             }
-            mbar_arrive(&bar_empty[mgroup][mwarp]);                // my rows of the buffer are free again (loads are complete)
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_empty[mgroup][mwarp]);   // my rows of the buffer are free again (every lane's loads are complete)
             // own state and constant row
 #pragma unroll
             for (int q = 0; q < NQ; ++q) {

@@ -163,8 +163,6 @@ int check_args(const gnn_graph* g, const gnn_mlp* net, const gnn_loop_args* a) {
     } else if (a->row_offset != 0 || a->exchange || a->n_peers > 1) {
         GNN_FAIL(GNN_ERR_INVALID, "row_offset / exchange / peers need n_global");
     }
-    for (int l = 0; l <= net->n_layers && l <= GNN_MAX_LAYERS; ++l)
-        if (net->drop_rate[l] > 0.f && a->training == 0) { /* inactive in inference */ }
     return GNN_OK;
 }
 
@@ -185,6 +183,9 @@ bool ws_applicable(const gnn_graph* g, const gnn_loop_args* a, const NetLayout& 
     const char* env = getenv("GNN_B200_KERNEL");
     if (env && !strcmp(env, "sym")) return false;
     if (lay.L != 1 || lay.DP < 16 || lay.DP > 32 || lay.CP > 16) return false;   // (constant row: at most two k-steps in registers)
+    // the loader warp stages row pointers / arc sources / scales with bulk copies: 16-byte aligned arrays
+    auto misaligned = [](const void* ptr) { return ptr && ((uintptr_t)ptr & 15) != 0; };
+    if (misaligned(g->rowptr) || misaligned(g->col) || misaligned(g->val) || misaligned(g->row_scale)) return false;
     if (a->training)
         for (int i = 0; i <= lay.L; ++i) if (lay.drop[i] > 0.f) return false;
     if (env && !strcmp(env, "ws")) return true;
@@ -331,7 +332,8 @@ extern "C" int gnn_state_loop_forward(const gnn_graph* g, const gnn_mlp* net, co
 
     IterParams p;
     memset(&p, 0, sizeof(p));
-    p.rowptr = g->rowptr; p.col = g->col; p.val = plan.has_val ? g->val : nullptr; p.N = N; p.row_offset = a->row_offset;
+    p.rowptr = g->rowptr; p.col = g->col; p.val = plan.has_val ? g->val : nullptr; p.row_scale = plan.has_val ? nullptr : g->row_scale;
+    p.N = N; p.E = g->n_arcs; p.row_offset = a->row_offset;
     p.cst = w.cst; p.wpack = w.wpack; p.k_ptr = kptr; p.thr = a->threshold; p.bn_partial = w.bn_partial;
     p.bn_train = bn_train; p.seed = a->seed; p.training = a->training; p.scol_cap = plan.scol_cap; p.ring_slots = plan.ring_slots; p.slot_rows = plan.slot_rows;
     { const char* dbg = getenv("GNN_B200_WS_DEBUG"); p.ws_debug = dbg ? atoi(dbg) : 0; } p.net = lay;

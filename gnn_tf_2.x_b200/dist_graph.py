@@ -190,13 +190,18 @@ class GraphPartition:
         # order this call after everything the peers did with the shared buffers in the previous call
         dist.all_reduce(self._order, op=dist.ReduceOp.MAX, group=self.group)
         if not self.fused: return
-        if self._state_offsets is None:
+        # The offset of the state buffers inside the workspace depends on max_iteration, the size of the packed net and the
+        # width of the constant rows: another GNN / LGNN layer over the same partition moves it.  The cache is keyed on the
+        # local layout; every rank runs the same program (same nets, same max_iteration), so all ranks re-gather together.
+        key = (id(self._ws), int(state_offset))
+        if self._state_offsets is None or self._state_offsets[0] != key:
             mine = torch.tensor([state_offset], dtype=torch.int64, device=self.device)
             every = [torch.zeros_like(mine) for _ in range(self.world)]
             dist.all_gather(every, mine, group=self.group)
-            self._state_offsets = [int(t.item()) for t in every]
+            self._state_offsets = (key, [int(t.item()) for t in every])
+        offsets = self._state_offsets[1]
         args.n_peers, args.rank = self.world, self.rank
-        for r in range(self.world): args.peer_state[r] = int(self._handle.buffer_ptrs[r]) + self._state_offsets[r]
+        for r in range(self.world): args.peer_state[r] = int(self._handle.buffer_ptrs[r]) + offsets[r]
         args.peer_mask = None if self._peer_mask is None else self._peer_mask.data_ptr()
 
     def exchange(self, t: int, x_full: torch.Tensor, go_flag: Optional[torch.Tensor]) -> None:

@@ -526,9 +526,12 @@ class GraphTensor:
 
     # cached index tensors (boolean_mask without a device->host sync at every step) ------------------------------------
     def _cached(self, name: str, build):
+        # keyed on storage address + in-place version counter: an in-place edit or a reassigned mask rebuilds the index
         cache = self.__dict__.setdefault('_index_cache', dict())
-        key = (name, id(self.set_mask), id(self.output_mask))
-        if key not in cache: cache[key] = build()
+        key = (name, self.set_mask.data_ptr(), self.set_mask._version, self.output_mask.data_ptr(), self.output_mask._version)
+        if key not in cache:
+            for old in [k for k in cache if k[0] == name]: del cache[old]
+            cache[key] = build()
         return cache[key]
 
     def mask_index(self):
@@ -561,8 +564,9 @@ class GraphTensor:
         """ (rowptr over graphs, node index, int64 graph ids) when the graph ids are non-decreasing, else None """
         import torch
         cache = self.__dict__.setdefault('_pool_cache', dict())
-        key = id(self._ng_ids)
+        key = (self._ng_ids.data_ptr(), self._ng_ids._version)
         if key not in cache:
+            cache.clear()
             ids = self._ng_ids.to(torch.int64)
             if ids.numel() > 1 and bool((ids[1:] < ids[:-1]).any()):
                 cache[key] = None

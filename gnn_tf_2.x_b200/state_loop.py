@@ -130,7 +130,9 @@ class _StateLoop(torch.autograd.Function):
         if failure: raise failure[0]
         if save:
             ctx.cfg, ctx.workspace, ctx.nbytes = cfg, workspace, nbytes.value
-            ctx.held = (x0c, nodes_c, agg_nodes_c, agg_arcs_c, x_out, k_out, keep)
+            # inputs only: keeping the Function's own outputs on ctx would close an output -> grad_fn -> ctx -> output cycle that
+            # pins the workspace (12.9 GB at C4) until the cycle collector runs; backward reads k from the workspace
+            ctx.held = (x0c, nodes_c, agg_nodes_c, agg_arcs_c, keep)
             ctx.need = (x0.requires_grad, nodes is not None and nodes.requires_grad, agg_nodes.requires_grad,
                         agg_arcs.requires_grad)
             ctx.n_params = len(params)
@@ -141,7 +143,7 @@ class _StateLoop(torch.autograd.Function):
     def backward(ctx, g_x, _g_k):
         lib = N.lib()
         cfg = ctx.cfg
-        x0c, nodes_c, agg_nodes_c, agg_arcs_c, x_out, k_out, _ = ctx.held
+        x0c, nodes_c, agg_nodes_c, agg_arcs_c, _ = ctx.held
         device = x0c.device
         n_nodes = int(x0c.shape[0])
         g_x = g_x.contiguous().to(torch.float32)
@@ -155,7 +157,7 @@ class _StateLoop(torch.autograd.Function):
         args.agg_nodes, args.agg_arcs = agg_nodes_c.data_ptr(), agg_arcs_c.data_ptr()
         args.max_iter, args.threshold = int(cfg.max_iter), float(cfg.threshold)
         args.training, args.save_for_backward, args.seed = int(bool(cfg.training)), 1, int(cfg.seed) & 0xFFFFFFFF
-        args.x_out, args.k_out = x_out.data_ptr(), k_out.data_ptr()
+        args.x_out = args.k_out = None        # not touched by the backward sweep
 
         # gradients of the trainable variables, Keras order: [kernel, bias] per Dense (+ gamma, beta)
         grad = N.gnn_mlp_grad()

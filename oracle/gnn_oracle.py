@@ -156,7 +156,7 @@ class OracleGraph:
     sample_weights: torch.Tensor
     adj: dict                          # transposed_row_major(Adjacency): rows = dst, cols = src
     arcnode: dict                      # transposed_row_major(ArcNode): rows = dst, cols = arc id
-    nodegraph: Optional[torch.Tensor]  # dense (N, G) or None
+    nodegraph: Optional[torch.Tensor]  # dense (N, G), or sparse COO (N, G) for large merged batches, or None
 
     @classmethod
     def build(cls, arcs, nodes, targets, problem_based='n', set_mask=None, output_mask=None, sample_weights=1,
@@ -172,11 +172,20 @@ class OracleGraph:
         ad_row, ad_col, ad_data = G.adjacency_coo(src, dst, an_data)
         if nodegraph is None: nodegraph = G.nodegraph(n_nodes, problem_based)
         f = lambda a: torch.tensor(np.asarray(a, dtype=np.float32), dtype=DTYPE)
+        if isinstance(nodegraph, tuple) and nodegraph[0] == 'segments':
+            # block-diagonal NodeGraph of a merged batch (graph_class.py:313-315) given as (graph id, coefficient) per node:
+            # the same matrix, held sparse -- the dense (N, G) array of 5 000 graphs x 150 000 nodes would take 3 GB
+            _, gid, coeff, n_graphs = nodegraph
+            idx = torch.stack([torch.arange(n_nodes), torch.as_tensor(np.asarray(gid, dtype=np.int64))])
+            ng = torch.sparse_coo_tensor(idx, f(coeff), (n_nodes, int(n_graphs))).coalesce()
+            nodegraph = None
+        else:
+            ng = None if nodegraph is None else f(nodegraph)
         return cls(nodes=f(nodes), arcs=f(arcs), targets=f(targets), set_mask=torch.tensor(set_mask),
                    output_mask=torch.tensor(output_mask), sample_weights=f(sample_weights * np.ones(targets.shape[0])),
                    adj=G.transposed_row_major(ad_row, ad_col, ad_data, (n_nodes, n_nodes)),
                    arcnode=G.transposed_row_major(an_row, an_col, an_data, (n_arcs, n_nodes)),
-                   nodegraph=None if nodegraph is None else f(nodegraph))
+                   nodegraph=ng)
 
 
 def spmm(sp: dict, dense: torch.Tensor, fast: bool = False) -> torch.Tensor:

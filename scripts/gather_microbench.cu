@@ -2,9 +2,11 @@
 // (the C4 shape), three mechanisms, several depths / occupancies.  Build: nvcc -arch=sm_100a -O3 -o gather_mb gather_microbench.cu
 #include <cstdio>
 #include <cstdlib>
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <vector>
+#include <cmath>
 
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %d\n", cudaGetErrorString(e), __LINE__); exit(1);} } while (0)
 
@@ -122,6 +124,104 @@ __global__ void gather_bulk(const float* __restrict__ x, const int* __restrict__
     }
 }
 
+
+// D / E: the ring pipeline of the fused kernel in isolation.  One persistent CTA per SM: a loader thread stages the arc sources of
+// each 16-node sub-tile (160 rows) in shared memory with ONE bulk copy, NIW issue warps land the rows in a ring of SLOTS sub-tile
+// slots, NCW consume warps sum them.  MODE 0: cp.async (LDGSTS) 16 B per lane, 4 rows per warp instruction, lean loop (index LDS,
+// address IMAD, copy).  MODE 1: TMA tile::gather4 (UTMALDG.2D.GATHER4), 4 rows per single-thread instruction.
+__device__ __forceinline__ unsigned s32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mb_init(uint64_t* b, int c) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s32(b)), "r"(c) : "memory"); }
+__device__ __forceinline__ void mb_arrive(uint64_t* b) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(b)) : "memory"); }
+__device__ __forceinline__ void mb_expect(uint64_t* b, int bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s32(b)), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void mb_wait(uint64_t* b, unsigned parity) {
+    unsigned done = 0, a = s32(b);
+    while (!done) asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(a), "r"(parity) : "memory");
+}
+template <int MODE, int NIW, int NCW, int SLOTS>
+__global__ void __launch_bounds__(32 * (1 + NIW + NCW), 1)
+gather_ring(const float* __restrict__ x, const __grid_constant__ CUtensorMap tm, const int* __restrict__ col, long long n_sub, float* __restrict__ out) {
+    constexpr int DEG = 10, SUB = 16, ROWS = DEG * SUB, NI = 2 * SLOTS;
+    extern __shared__ __align__(128) unsigned char smraw[];
+    float* land = reinterpret_cast<float*>(smraw);                                   // [SLOTS][ROWS][32]
+    int* sidx = reinterpret_cast<int*>(smraw + (size_t)SLOTS * ROWS * 128);         // [NI][ROWS]
+    __shared__ __align__(8) uint64_t landed[SLOTS], freeb[SLOTS], idxb[NI], idxfree[NI];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < SLOTS; ++i) { mb_init(&landed[i], MODE == 0 ? 32 : 1); mb_init(&freeb[i], 1); }
+        for (int i = 0; i < NI; ++i) { mb_init(&idxb[i], 1); mb_init(&idxfree[i], 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const long long s0 = n_sub * blockIdx.x / gridDim.x, s1 = n_sub * (blockIdx.x + 1) / gridDim.x;
+    const int cnt = (int)(s1 - s0);
+    if (warp == 0) {
+        if (lane == 0)
+            for (int j = 0; j < cnt; ++j) {
+                const int q = j % NI;
+                if (j >= NI) mb_wait(&idxfree[q], ((j / NI) - 1) & 1);
+                mb_expect(&idxb[q], ROWS * 4);
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(s32(sidx + q * ROWS)), "l"(col + (s0 + j) * ROWS), "r"(ROWS * 4), "r"(s32(&idxb[q])) : "memory");
+            }
+    } else if (warp <= NIW) {
+        const int w = warp - 1;
+        for (int j = w; j < cnt; j += NIW) {
+            const int q = j % NI, slot = j % SLOTS;
+            mb_wait(&idxb[q], (j / NI) & 1);
+            if (j >= SLOTS) mb_wait(&freeb[slot], ((j / SLOTS) - 1) & 1);
+            const int* si = sidx + q * ROWS;
+            float* lb = land + (size_t)slot * ROWS * 32;
+            if (MODE == 0) {
+                const int g = lane >> 3, l8 = lane & 7;
+                const float* xl = x + 4 * l8;
+                float* db = lb + 4 * l8;
+#pragma unroll 8
+                for (int r = g; r < ROWS; r += 4) {
+                    const int s = si[r];
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s32(db + r * 32)), "l"(xl + (size_t)s * 32));
+                }
+                asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(s32(&landed[slot])) : "memory");
+                __syncwarp();
+                if (lane == 0) mb_arrive(&idxfree[q]);
+            } else {
+                if (lane == 0) {
+                    mb_expect(&landed[slot], ROWS * 128);
+                    const int4* s4 = reinterpret_cast<const int4*>(si);
+#pragma unroll 4
+                    for (int r = 0; r < ROWS / 4; ++r) {
+                        const int4 s = s4[r];
+                        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+                                     ::"r"(s32(lb + r * 128)), "l"(&tm), "r"(s32(&landed[slot])), "r"(0), "r"(s.x), "r"(s.y), "r"(s.z), "r"(s.w) : "memory");
+                    }
+                    mb_arrive(&idxfree[q]);
+                }
+                __syncwarp();
+            }
+        }
+        if (MODE == 0) asm volatile("cp.async.wait_all;" ::: "memory");
+    } else {
+        const int c = warp - 1 - NIW, g = lane >> 3, l8 = lane & 7;
+        for (int j = c; j < cnt; j += NCW) {
+            const int slot = j % SLOTS;
+            mb_wait(&landed[slot], (j / SLOTS) & 1);
+            const float* lb = land + (size_t)slot * ROWS * 32 + 4 * l8;
+#pragma unroll
+            for (int u = 0; u < SUB / 4; ++u) {
+                const int node = g + 4 * u;
+                float4 acc = make_float4(0, 0, 0, 0);
+#pragma unroll
+                for (int e = 0; e < DEG; ++e) {
+                    const float4 r = *reinterpret_cast<const float4*>(lb + (node * DEG + e) * 32);
+                    acc.x += r.x; acc.y += r.y; acc.z += r.z; acc.w += r.w;
+                }
+                *reinterpret_cast<float4*>(out + ((s0 + j) * SUB + node) * 32 + 4 * l8) = acc;
+            }
+            __syncwarp();
+            if (lane == 0) mb_arrive(&freeb[slot]);
+        }
+    }
+}
+
 int main(int argc, char** argv) {
     const long long N = 1000000; const int DEG = 10; const long long E = N * DEG;
     const int local = argc > 1 ? atoi(argv[1]) : 0;   // 0: uniform sources, else +-local window
@@ -164,6 +264,36 @@ int main(int argc, char** argv) {
             snprintf(nm, 96, "C cp.async.bulk 128B rows, 8 nodes x 3 stages/warp, %d CTAs/SM", ctas);
             TIME(nm, (gather_bulk<10, NPS, ST><<<sms * ctas, thr, smb>>>(x, col, N, out)));
         }
+    }
+
+    {
+        // checksum of variant A as the reference for D / E
+        std::vector<float> hx(N * 32);
+        for (size_t i = 0; i < hx.size(); ++i) hx[i] = (float)((i * 2654435761u) % 1000) * 1e-3f;
+        CK(cudaMemcpy(x, hx.data(), N * 128, cudaMemcpyHostToDevice));
+        std::vector<float> ref(N * 32), got(N * 32);
+        gather_ldg<10><<<sms * 16, 128>>>(x, col, DEG, N, out);
+        CK(cudaMemcpy(ref.data(), out, N * 128, cudaMemcpyDeviceToHost));
+        CUtensorMap tm;
+        cuuint64_t gdim[2] = {32, (cuuint64_t)N}, gstr[1] = {128};
+        cuuint32_t box[2] = {32, 1}, estr[2] = {1, 1};
+        CUresult cr = cuTensorMapEncodeTiled(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, x, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr != CUDA_SUCCESS) { printf("cuTensorMapEncodeTiled failed: %d\n", (int)cr); return 1; }
+        const long long n_sub = N / 16;
+        auto check = [&](const char* nm) {
+            CK(cudaMemcpy(got.data(), out, N * 128, cudaMemcpyDeviceToHost));
+            double md = 0; for (size_t i = 0; i < got.size(); ++i) md = fmax(md, fabs((double)got[i] - ref[i]));
+            printf("    %s max |diff| vs A = %.3g\n", nm, md);
+        };
+#define RING(MODE, NIW, NCW, SLOTS) { \
+            size_t smr = (size_t)SLOTS * 160 * 128 + 2 * SLOTS * 160 * 4; \
+            CK(cudaFuncSetAttribute(gather_ring<MODE, NIW, NCW, SLOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smr)); \
+            char nm[128]; snprintf(nm, 128, "%s ring %d slots, %d issue + %d consume warps", MODE ? "D gather4" : "E cp.async", SLOTS, NIW, NCW); \
+            CK(cudaMemset(out, 0, N * 128)); \
+            TIME(nm, (gather_ring<MODE, NIW, NCW, SLOTS><<<sms, 32 * (1 + NIW + NCW), smr>>>(x, tm, col, n_sub, out))); check(nm); }
+        RING(0, 4, 8, 8) RING(0, 2, 8, 8) RING(0, 8, 8, 8) RING(0, 2, 10, 10) RING(0, 4, 4, 8) RING(0, 4, 4, 4)
+        RING(1, 4, 8, 8) RING(1, 2, 8, 8) RING(1, 8, 8, 8) RING(1, 1, 8, 8) RING(1, 2, 10, 10)
     }
     // streaming reference: read x once, write out once
     CK(cudaMemcpy(out, x, N * 128, cudaMemcpyDeviceToDevice));
