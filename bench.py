@@ -105,18 +105,24 @@ def make_graph_batches(n_graphs: int, graphs_per_step: int, seed: int = 0):
 
 
 def bench_graph_batches(args, device, rank, world):
-    """ C5 leg: graph batches sharded by whole graph over the ranks (weak scaling: 25 000 graphs per rank), one
-    training_step (forward + BPTT + flat gradient all-reduce + Adam) per merged batch """
+    """ C5 leg: 200 000 MUTAG-shaped graphs as merged batches of 25 000, sharded by whole batch over the ranks (STRONG scaling: the
+    same dataset at every N; N = 1 trains all of it).  One training_step (forward + BPTT + flat gradient all-reduce + Adam) per
+    batch, each captured once as a CUDA graph and replayed; step = one epoch of the rank's shard """
     import torch
     import torch.distributed as dist
     from gnn_b200 import _native
     from gnn_b200.graph_class import GraphTensor
     from gnn_b200.GNN import GNNgraphBased
     from gnn_b200.keras_compat import Dense, Sequential, Adam, categorical_crossentropy
-    per_rank, per_step = args.graphs_per_rank, args.graphs_per_step
-    batches = make_graph_batches(per_rank, per_step, seed=1000 + rank)
-    gts = [GraphTensor.fromGraphObject(b, device=device) for b in batches]
-    arcs = sum(int(b.arcs.shape[0]) for b in batches)
+    total, per_step = args.graphs_total, args.graphs_per_step
+    n_batches = max(world, total // per_step)
+    mine = [b for b in range(n_batches) if b * world // n_batches == rank]          # contiguous blocks of batches per rank
+    gts, arcs = [], 0
+    for b in mine:                                   # the dataset does not depend on N: batch b is always drawn from seed 1000 + b
+        g = make_graph_batches(per_step, per_step, seed=1000 + b)[0]
+        arcs += int(g.arcs.shape[0])
+        gts.append(GraphTensor.fromGraphObject(g, device=device))
+        del g
     rng = np.random.default_rng(0)     # identical (replicated) initial weights on every rank
     net_s = Sequential([Dense(14, activation='selu')], input_dim=31, device=device)
     net_o = Sequential([Dense(2, activation='softmax')], input_dim=14, device=device)
@@ -125,6 +131,7 @@ def bench_graph_batches(args, device, rank, world):
     gnn = GNNgraphBased(net_s, net_o, Adam(1e-3), categorical_crossentropy, {'from_logits': False}, state_vect_dim=0, max_iteration=5,
                         threshold=0.01, addressed_problem='c', path_writer=f'/tmp/gnn_b200_bench_c5_{rank}/')
     gnn.distributed = world > 1
+    gnn.use_cuda_graph = not args.no_cuda_graph
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ks = []
 
@@ -133,7 +140,7 @@ def bench_graph_batches(args, device, rank, world):
             iters, _ = gnn.training_step(gt)
             ks.append(iters[0])
 
-    for _ in range(max(1, args.warmup // 3)): epoch()
+    for _ in range(max(3, args.warmup)): epoch()     # (CUDA graph: two eager steps + the capture of every batch happen here)
     torch.cuda.synchronize()
     if world > 1: dist.barrier()
     _native.launch_count(reset=True)
@@ -143,16 +150,24 @@ def bench_graph_batches(args, device, rank, world):
     torch.cuda.synchronize()
     if world > 1: dist.barrier()
     ms = torch.tensor([start.elapsed_time(stop) / args.steps], device=device)
-    upd = torch.tensor([float(sum(float(k) for k in ks[-len(gts):]) / len(gts)) * arcs], device=device)   # arcs x iterations of one epoch
+    upd = torch.tensor([float(sum(float(k) for k in ks[-len(gts):]) / max(len(gts), 1)) * arcs], device=device)   # arcs x iterations of one epoch
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(upd, op=dist.ReduceOp.SUM)
-    return {'value': float(upd.item()) / (float(ms.item()) * 1e-3), 'ms_per_step': float(ms.item()), 'epoch_time_s': float(ms.item()) * 1e-3,
-            'gpu_launches': int(_native.launch_count() // args.steps),
-            'config': {'workload': f'c5: {per_rank} MUTAG-shaped graphs per rank ({per_rank * world} in total), merged batches of {per_step}, '
-                                   f'graph classification, NL 14, AL 3, state = labels (D 14), max_iteration 5, threshold 0.01, one '
-                                   f'training_step (forward + BPTT + gradient all-reduce + Adam) per batch; step = one epoch of the shard',
-                       'arcs_per_rank': arcs}}
+    # fwd + bwd algorithmic bytes per arc-update of this shape (67 B forward; backward 4 E + N (4 + 16 D + 12)): ~190 B
+    value = float(upd.item()) / (float(ms.item()) * 1e-3)
+    peak = 6553.9
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f: peak = float(json.load(f).get('hbm_gbs', peak))
+    except Exception:
+        pass
+    return {'value': value, 'ms_per_step': float(ms.item()), 'epoch_time_s': float(ms.item()) * 1e-3,
+            'gpu_launches': int(_native.launch_count() // args.steps), 'roofline_frac': value * 190.0 / 1e9 / (peak * world),
+            'config': {'workload': f'c5: {n_batches * per_step} MUTAG-shaped graphs in merged batches of {per_step}, sharded by whole batch over {world} '
+                                   f'rank(s) ({len(mine)} batch(es) per rank), graph classification, NL 14, AL 3, state = labels (D 14), max_iteration 5, '
+                                   f'threshold 0.01; one training_step (forward + BPTT + gradient all-reduce + Adam) per batch, '
+                                   f'{"replayed as a CUDA graph" if gnn.use_cuda_graph else "eager launches"}; step = one epoch of the dataset',
+                       'arcs_per_rank': arcs, 'l2': 'inputs larger than L2 (25 000 graphs = 760k nodes x 56-byte rows x 11 saved iterates)'}}
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -286,6 +301,133 @@ def parity_check(wl, gnn, gt, device, iterations: int, training: bool, tol: floa
             'elementwise_rel_p99': max(e[1] for e in errs.values()), 'elementwise_rel_max': max(e[2] for e in errs.values()),
             'per_tensor_max_rel': {n: e[0] for n, e in errs.items()}, 'kernel': None}
 
+
+# ---------------------------------------------------------------------------------------------------------------------
+# configs 1-3 of BASELINE.json: small-graph training through the reference's own API (epoch time + steps/s)
+# ---------------------------------------------------------------------------------------------------------------------
+def make_small_dataset(kind: str, seed: int = 0):
+    """ c1 / c3: starter.py:31-40 -- 100 random graphs, N ~ U{15..39}, NL 3, AL 1, T 2, density .7, node-focused, split
+    .7 / .1 / .2 by getindices, training batches of 32 merged graphs.  c2: 4337 MUTAG-shaped graphs (the bundled dataset's size;
+    NL 14 / AL 3 one-hot, T 2, graph-focused), one of the ten LKO folds: 9/10 of the graphs train, batches of 32. """
+    from gnn_b200 import GNN_utils as utils
+    np.random.seed(seed)
+    if kind in ('c1', 'c3'):
+        graphs = [utils.randomGraph(int(np.random.choice(range(15, 40))), 3, 1, 2, 0.7, problem_based='n') for _ in range(100)]
+        iTr, iTe, iVa = utils.getindices(len(graphs), 0.7, 0.1, seed=seed)
+        gTr = utils.getbatches([graphs[i] for i in iTr], 'n', 'average', batch_size=32)
+        return gTr, 'n', 3, 1, 2
+    graphs = []
+    for b in make_graph_batches(4337, 1, seed=seed): graphs.append(b)
+    fold = len(graphs) // 10
+    gTr = utils.getbatches(graphs[fold:], 'g', 'average', batch_size=32)
+    return gTr, 'g', 14, 3, 2
+
+
+def build_small_model(kind: str, problem: str, NL: int, AL: int, T: int, device, path: str):
+    """ nets per starter.py:52-69 (selu + lecun_normal state net with BatchNormalization and Dropout(0.1) at position 0; softmax +
+    glorot_normal output net -- WITHOUT the trailing BatchNormalization: with T = 2 it makes the two outputs exact opposites and
+    every loss NaN, in the reference too), state_vect_dim 0, max_iteration 5, threshold 0.01, Adam(1e-3); c3: 5 layers,
+    get_state False / get_output True (starter.py:77-79) """
+    from gnn_b200.MLP import MLP, get_inout_dims
+    from gnn_b200.GNN import GNNnodeBased, GNNgraphBased
+    from gnn_b200.LGNN import LGNN
+    from gnn_b200.keras_compat import Adam, categorical_crossentropy
+    cls = {'n': GNNnodeBased, 'g': GNNgraphBased}[problem]
+
+    def one(layer, seed):
+        kw = dict(layer=layer, get_state=False, get_output=True) if kind == 'c3' else dict()
+        f_s, l_s = get_inout_dims('state', NL, AL, T, problem, 0, None, **kw)
+        f_o, l_o = get_inout_dims('output', NL, AL, T, problem, 0, None, **kw)
+        net_s = MLP(f_s, l_s, 'selu', 'lecun_normal', 'lecun_normal', dropout_rate=0.1, dropout_pos=0, batch_normalization=True, device=device, seed=seed)
+        net_o = MLP(f_o, l_o, 'softmax', 'glorot_normal', 'glorot_normal', dropout_rate=0.1, dropout_pos=0, batch_normalization=False, device=device, seed=seed + 1)
+        return cls(net_s, net_o, Adam(1e-3), categorical_crossentropy, {'from_logits': False}, state_vect_dim=0, max_iteration=5, threshold=0.01,
+                   addressed_problem='c', path_writer=f'{path}{layer}/')
+
+    if kind != 'c3': return one(0, 10)
+    return LGNN([one(l, 10 + 2 * l) for l in range(5)], False, True, Adam(1e-3), categorical_crossentropy, {'from_logits': False}, 'c', path_writer=f'{path}lgnn/')
+
+
+def cpu_port_small(kind, gTr, problem, weights):
+    """ one epoch of forward + BPTT gradients (no optimizer) of the oracle port on the same batches, all host threads """
+    import torch
+    from oracle import gnn_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    graphs = []
+    for g in gTr:
+        ng = None
+        if problem == 'g':
+            gid, coeff, G = g.nodegraph_segments()
+            ng = ('segments', gid, coeff, G)
+        graphs.append(O.OracleGraph.build(g.arcs, g.nodes, g.targets, problem, g.set_mask, g.output_mask, g.sample_weights, ng, 'average', endpoints=(g._src, g._dst)))
+    nets = [(O.OracleMLP.from_weights(ws, ['selu'], drop=[0.1, 0.0], batchnorm=True), O.OracleMLP.from_weights(wo, ['softmax'], drop=[0.1, 0.0])) for ws, wo in weights]
+    t0 = time.perf_counter()
+    for og in graphs:
+        if kind == 'c3':
+            O.lgnn_training_gradients(og, nets, O.categorical_crossentropy, training_mode='parallel', mean=True, get_state=False, get_output=True,
+                                      state_vect_dim=0, max_iteration=5, threshold=0.01, x0s=[None] * 5, problem_based=problem)
+        else:
+            O.training_gradients(og, nets[0][0], nets[0][1], O.categorical_crossentropy, mean=True, state_vect_dim=0, max_iteration=5, threshold=0.01,
+                                 problem_based=problem)
+    return time.perf_counter() - t0, os.cpu_count() or 1
+
+
+def bench_small(args, device):
+    """ --workload c1 | c2 | c3: epoch time and training steps per second of gnn.train's inner loop (one training_step per merged
+    batch of 32 graphs: forward loop, BPTT, Adam), eager launches and CUDA-graph replay, CPU port beside """
+    import torch
+    from gnn_b200 import _native
+    from gnn_b200.graph_class import GraphTensor
+    kind = args.workload
+    gTr, problem, NL, AL, T = make_small_dataset(kind)
+    gts = [GraphTensor.fromGraphObject(g, device=device) for g in gTr]
+    arcs = sum(int(g.arcs.shape[0]) for g in gTr)
+    modes = ['parallel', 'residual'] if kind == 'c3' else [None]     # serial = the single-GNN numbers, layer after layer
+    out = {}
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    weights = None
+    for mode in modes:
+        for graphed in (False, True):
+            model = build_small_model(kind, problem, NL, AL, T, device, f'/tmp/gnn_b200_bench_{kind}/')
+            if mode: model.training_mode = mode
+            if weights is None:
+                gl = model.gnns if kind == 'c3' else [model]
+                weights = [(m.net_state.get_weights(), m.net_output.get_weights()) for m in gl]
+            model.use_cuda_graph = graphed
+            ks = []
+
+            def epoch():
+                for gt in gts:
+                    iters, _ = model.training_step(gt)
+                    ks.append(iters)
+
+            for _ in range(max(3, args.warmup)): epoch()        # (graphed: two eager steps + the capture happen here)
+            torch.cuda.synchronize()
+            _native.launch_count(reset=True)
+            start.record()
+            for _ in range(args.steps): epoch()
+            stop.record()
+            torch.cuda.synchronize()
+            ms = start.elapsed_time(stop) / args.steps
+            k_mean = float(np.mean([float(k) for it in ks[-len(gts):] for k in it]))
+            out[(mode or 'gnn') + ('+cuda_graph' if graphed else '+eager')] = {
+                'epoch_time_s': ms * 1e-3, 'steps_per_s': len(gts) / (ms * 1e-3), 'arc_updates_per_s': arcs * k_mean / (ms * 1e-3), 'mean_iterations': k_mean}
+    cpu = None
+    if not args.skip_cpu:
+        sec, threads = cpu_port_small(kind, gTr, problem, weights)
+        cpu = {'value': len(gTr) / sec, 'unit': 'training steps/s', 'epoch_time_s': sec, 'cores': threads, 'kind': 'port',
+               'sample': 'one epoch of forward + BPTT gradients (no optimizer step) on the same batches',
+               'note': 'torch-CPU restatement of the reference TF2 path (oracle/), not TensorFlow'}
+    best = max(out, key=lambda name: out[name]['steps_per_s'])
+    names = {'c1': 'config 1: starter.py default GNN, node-focused, 100 random graphs (70 train), batches of 32',
+             'c2': 'config 2: MUTAG-shaped graph-focused GNN with NodeGraph pooling, one LKO fold of 4337 graphs (3904 train), batches of 32',
+             'c3': 'config 3: 5-layer LGNN (get_output) on the config-1 data, parallel / residual modes'}
+    print(json.dumps({'metric': 'training steps/s (one training_step per merged batch of 32 graphs); epoch time', 'value': out[best]['steps_per_s'],
+                      'unit': 'training steps/s', 'n_gpus': 1, 'steps': args.steps, 'warmup': max(3, args.warmup), 'ms_per_step': out[best]['epoch_time_s'] * 1e3,
+                      'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+                      'config': {'workload': names[kind], 'batches_per_epoch': len(gts), 'arcs_per_epoch': arcs, 'best': best,
+                                 'l2': 'working set smaller than L2 by nature (a few thousand arcs per batch)'},
+                      'variants': out, 'cpu_baseline': cpu}))
+
 # ---------------------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -293,9 +435,10 @@ def main():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--workload', default='c4u', choices=['c4u', 'c4l', 'c5'])
-    ap.add_argument('--graphs-per-rank', type=int, default=25_000)
-    ap.add_argument('--graphs-per-step', type=int, default=5_000)
+    ap.add_argument('--workload', default='c4u', choices=['c4u', 'c4l', 'c5', 'c1', 'c2', 'c3'])
+    ap.add_argument('--graphs-total', type=int, default=200_000)
+    ap.add_argument('--graphs-per-step', type=int, default=25_000)
+    ap.add_argument('--no-cuda-graph', action='store_true', help='graph batches: eager launches instead of one CUDA graph per batch')
     ap.add_argument('--nodes', type=int, default=1_000_000)
     ap.add_argument('--arcs', type=int, default=10_000_000)
     ap.add_argument('--max-iter', type=int, default=50)
@@ -351,12 +494,16 @@ def main():
         dist.init_process_group('nccl', device_id=device)
 
     from gnn_b200 import dist_graph
+    if args.workload in ('c1', 'c2', 'c3'):      # small-graph training through the reference API (single GPU)
+        if rank == 0: bench_small(args, device)
+        if world > 1: dist.destroy_process_group()
+        return
     if args.workload == 'c5':   # graph-batch sharding (weak scaling); not the headline workload
         with ClockSampler(local_rank) as clocks:
             res = bench_graph_batches(args, device, rank, world)
         if rank == 0:
             res.update({'metric': 'arc-updates/sec (arcs x iterations), forward+backward+optimizer, sharded graph batches', 'unit': 'arc-updates/s',
-                        'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'higher_is_better': True, 'scaling': 'weak',
+                        'n_gpus': world, 'steps': args.steps, 'warmup': max(3, args.warmup), 'higher_is_better': True, 'scaling': 'strong',
                         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'clocks': clocks.summary()})
             print(json.dumps(res))
         if world > 1: dist.destroy_process_group()
@@ -392,8 +539,9 @@ def main():
         batches = None
         if not args.skip_variant:
             r5 = bench_graph_batches(args, device, rank, world)
-            batches = {'workload': r5['config']['workload'], 'scaling': 'weak', 'value': r5['value'], 'unit': 'arc-updates/s (forward+backward+Adam)',
-                       'ms_per_step': r5['ms_per_step'], 'arcs_per_rank': r5['config']['arcs_per_rank']}
+            batches = {'workload': r5['config']['workload'], 'scaling': 'strong', 'value': r5['value'], 'unit': 'arc-updates/s (forward+backward+Adam)',
+                       'ms_per_step': r5['ms_per_step'], 'arcs_per_rank': r5['config']['arcs_per_rank'], 'roofline_frac': r5['roofline_frac'],
+                       'gpu_launches': r5['gpu_launches']}
         if rank == 0:
             result['source_distribution_variant'] = variant
             result['graph_batches'] = batches
@@ -440,7 +588,7 @@ def main():
     with ClockSampler(local_rank) as clocks:
         _native.launch_count(reset=True)
         ms_fwd = timed(fwd, args.steps, max(3, args.warmup))
-        launches_fwd = _native.launch_count() * args.steps // (args.steps + max(3, args.warmup))
+        launches_fwd = _native.launch_count() // (args.steps + max(3, args.warmup))      # library kernels per step (one forward loop)
         k_fwd = float(ks[-1])
         value = E * k_fwd / (ms_fwd * 1e-3)
 
@@ -465,8 +613,9 @@ def main():
                 'frac': achieved / peak_gbs, 'traffic': None, 'peak_source': 'MEASURED_PEAKS.json' if peaks else 'fallback 6650 GB/s',
                 'algorithmic_bytes_per_launch': alg_bytes, 'bytes_per_arc_update': alg_bytes / E, 'ms_per_launch': kernel_ms}
     traffic_file = os.path.join(ROOT, 'profiles', 'traffic_bytes_per_launch.json')
-    if os.path.exists(traffic_file):
+    if os.path.exists(traffic_file):     # DRAM bytes per launch from the committed `ncu --set full` capture of this kernel (not measured in this run)
         with open(traffic_file) as f: roofline['traffic'] = json.load(f).get(args.workload)
+        roofline['traffic_source'] = 'static: dram__bytes_read.sum + dram__bytes_write.sum of the ncu capture summarised in profiles/'
 
     # --- e2e: host buffers -> gnn(GraphObject) -> host outputs, every step -----------------------------------------
     g_host.pin_host_buffers()
@@ -496,8 +645,9 @@ def main():
 
         _native.launch_count(reset=True)
         ms_train = timed(train_step, max(1, args.steps // 2), 1)
+        launches_train = _native.launch_count() // (max(1, args.steps // 2) + 1)
         train = {'value': E * float(kt[-1]) / (ms_train * 1e-3), 'unit': 'arc-updates/s (forward+backward+Adam)', 'ms_per_step': ms_train,
-                 'epoch_time_s': ms_train * 1e-3, 'k': float(kt[-1])}
+                 'epoch_time_s': ms_train * 1e-3, 'k': float(kt[-1]), 'gpu_launches': int(launches_train)}
 
     # --- the other source distribution, forward loop only (U and L side by side) --------------------------
     variant = None
@@ -537,8 +687,9 @@ def main():
     batches = None
     if not args.skip_variant:
         r5 = bench_graph_batches(args, device, rank, world)
-        batches = {'workload': r5['config']['workload'], 'scaling': 'weak', 'value': r5['value'], 'unit': 'arc-updates/s (forward+backward+Adam)',
-                   'ms_per_step': r5['ms_per_step'], 'arcs_per_rank': r5['config']['arcs_per_rank']}
+        batches = {'workload': r5['config']['workload'], 'scaling': 'strong', 'value': r5['value'], 'unit': 'arc-updates/s (forward+backward+Adam)',
+                   'ms_per_step': r5['ms_per_step'], 'arcs_per_rank': r5['config']['arcs_per_rank'], 'roofline_frac': r5['roofline_frac'],
+                   'gpu_launches': r5['gpu_launches']}
 
     # --- CPU baseline: oracle port on the host cores, bounded sample ----------------------------------------------
     cpu = None

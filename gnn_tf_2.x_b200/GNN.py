@@ -186,9 +186,23 @@ class GNNnodeBased(BaseClass):
         if self.state_vect_dim: state_converged = torch.cat([state_converged, nodes], dim=1)
         return state_converged.index_select(0, mask_index)
 
-    def _next_seed(self) -> int:
+    def _next_seed(self):
+        """ dropout seed of the next call.  Inside a captured training step (BaseClass.training_step with use_cuda_graph) the
+        call counter lives on the device: the value is advanced by a captured op and handed to the kernels as a tensor """
         self._calls += 1
+        state = getattr(self, '_seed_state', None)
+        if state is not None:
+            state.add_(0x85EBCA77).bitwise_and_(0xFFFFFFFF)
+            return state.clone()              # this call's own copy: forward and backward kernels of the call read the same value
         return (self.dropout_seed * 0x9E3779B1 + self._calls * 0x85EBCA77) & 0xFFFFFFFF
+
+    def _device_seed(self, enable: bool, device=None) -> None:
+        """ switch the dropout call counter between host (python int) and device (int64 tensor) """
+        if enable:
+            start = (self.dropout_seed * 0x9E3779B1 + self._calls * 0x85EBCA77) & 0xFFFFFFFF
+            self._seed_state = torch.full((), start, dtype=torch.int64, device=device)
+        else:
+            self._seed_state = None
 
     def _state_and_inputs(self, g: GraphTensor):
         """ prologue of Loop (GNN.py:257-268) """

@@ -108,7 +108,17 @@ class BaseClass(ABC):
     def training_step(self, g: GraphTensor, mean: bool = True):
         """ one optimizer step on one (batch) graph (GNN_BaseClass.py:231-247): BPTT gradient of the summed loss
         (+ regularisers); net_state gradients divided by the iteration count when ``mean``.
+        With ``self.use_cuda_graph = True`` the whole step (prologue SpMMs, the loop's launches, output net, loss, backward
+        sweep, gradient all-reduce, optimizer) is captured ONCE per batch graph into a CUDA graph and replayed afterwards:
+        one launch per step instead of a hundred (the iteration count, the dropout seeds and the Adam step counter live on
+        the device, so a replay is a genuine new step).
         :return: (iterations, loss) as device tensors -- nothing is synchronised """
+        if getattr(self, 'use_cuda_graph', False) and g.device.type == 'cuda':
+            return self._graphed_training_step(g, mean)
+        return self._training_step_eager(g, mean)
+
+    def _step_gradients(self, g: GraphTensor, mean: bool):
+        """ forward + BPTT: (iterations, loss, gradients in the order of `flat`, flat list of the trainable variables) """
         iters, loss, *_ = self.evaluate_single_graph(g, training=True)
         loss = loss + self._regularizer_terms()
         wS, wO = self.trainable_variables()
@@ -116,7 +126,6 @@ class BaseClass(ABC):
         grads = torch.autograd.grad(loss, flat, allow_unused=True)
         grads = [torch.zeros_like(v) if gr is None else gr for v, gr in zip(flat, grads)]
         if not isinstance(iters, list): iters = [iters]
-        distributed = getattr(self, 'distributed', False)
         pos, dW = 0, []
         for layer_idx, layer in enumerate(wS):
             for _ in layer:
@@ -124,11 +133,65 @@ class BaseClass(ABC):
                 pos += 1
         dW += grads[pos:]
         assert len(dW) == len(flat)
-        if distributed:   # graph batches sharded by whole graph over the ranks: one all-reduce of the flat gradient
+        return iters, loss.detach(), dW, flat
+
+    def _training_step_eager(self, g: GraphTensor, mean: bool = True):
+        iters, loss, dW, flat = self._step_gradients(g, mean)
+        if getattr(self, 'distributed', False):   # graph batches sharded by whole graph over the ranks: one all-reduce of the flat gradient
             from .dist_graph import allreduce_gradients
             dW = allreduce_gradients(dW, getattr(self, 'process_group', None))
         self.optimizer.apply_gradients(zip(dW, flat))
-        return iters, loss.detach()
+        return iters, loss
+
+    def _seeded_models(self) -> list:
+        """ the GNNs whose dropout call counter must live on the device inside a captured step """
+        return list(getattr(self, 'gnns', [self]))
+
+    def _graphed_training_step(self, g: GraphTensor, mean: bool):
+        """ capture-and-replay of the training step for one batch graph (cache on the GraphTensor, keyed by model and `mean`).
+        Replaces the eager while_loop / GradientTape replay of GNN.py:271-272 + GNN_BaseClass.py:233-247 by one graph launch.
+        Single process: the optimizer step is part of the graph.  Sharded graph batches (self.distributed): the graph ends with
+        the flat gradient; the NCCL all-reduce and the optimizer follow it on the stream (two more launches, no host sync). """
+        cache = g.__dict__.setdefault('_step_graphs', dict())
+        key = (id(self), bool(mean))
+        entry = cache.get(key)
+        distributed = bool(getattr(self, 'distributed', False))
+        if entry is None:
+            if not hasattr(self.optimizer, 'capturable'):
+                raise NotImplementedError('use_cuda_graph needs an optimizer whose step is free of host state (keras_compat.Adam)')
+            self.optimizer.capturable = True
+            for m in self._seeded_models():
+                if getattr(m, '_seed_state', None) is None: m._device_seed(True, g.device)
+            # two eager steps on a side stream first (PyTorch's capture protocol: lazy initialisation, allocator warm-up, optimizer
+            # slots) -- they are real training steps, not discarded work
+            side = torch.cuda.Stream(device=g.device)
+            side.wait_stream(torch.cuda.current_stream(g.device))
+            with torch.cuda.stream(side):
+                for _ in range(2): out = self._training_step_eager(g, mean)
+            torch.cuda.current_stream(g.device).wait_stream(side)
+            cache[key] = ('warm',)
+            return out
+        if entry[0] == 'warm':
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                iters, loss, dW, flat = self._step_gradients(g, mean)
+                if distributed:
+                    packed = torch.cat([d.reshape(-1) for d in dW])
+                else:
+                    packed = None
+                    self.optimizer.apply_gradients(zip(dW, flat))
+            entry = cache[key] = ('graph', graph, iters, loss, packed, flat)
+        _, graph, iters, loss, packed, flat = entry
+        graph.replay()
+        if distributed:
+            import torch.distributed as dist
+            dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=getattr(self, 'process_group', None))
+            views, pos = [], 0
+            for v in flat:
+                views.append(packed[pos:pos + v.numel()].view_as(v))
+                pos += v.numel()
+            self.optimizer.apply_gradients(zip(views, flat))
+        return iters, loss           # static tensors of the captured step: valid until the next replay
 
     def train(self, gTr, epochs: int, gVa=None, update_freq: int = 10, max_fails: int = 10, observed_metric='Loss',
               policy='min', *, mean: bool = True, verbose: int = 3) -> None:

@@ -52,7 +52,8 @@ class gnn_loop_args(C.Structure):
                 ('save_for_backward', C.c_int32), ('seed', C.c_uint32),
                 ('x_out', C.c_void_p), ('k_out', C.c_void_p),
                 ('n_global', C.c_int64), ('row_offset', C.c_int64), ('exchange', C.c_void_p), ('exchange_user', C.c_void_p),
-                ('n_peers', C.c_int32), ('rank', C.c_int32), ('peer_state', C.c_void_p * 8), ('peer_mask', C.c_void_p)]
+                ('n_peers', C.c_int32), ('rank', C.c_int32), ('peer_state', C.c_void_p * 8), ('peer_mask', C.c_void_p),
+                ('seed_dev', C.c_void_p)]
 
 
 # callback type of gnn_loop_args.exchange: (user, t, x_next_offset, go_next_offset)
@@ -124,6 +125,16 @@ def _stream(device) -> int:
 
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
+
+
+def set_seed(args: 'gnn_loop_args', seed) -> None:
+    """ dropout seed of a call: python int (by value) or an int64 CUDA tensor holding a value in [0, 2^32) -- the kernels then read
+    its low 32 bits from device memory at run time (gnn_loop_args.seed_dev), which is what a CUDA-graph replay needs """
+    if isinstance(seed, torch.Tensor):
+        if seed.dtype != torch.int64 or not seed.is_cuda or seed.numel() != 1: raise TypeError('device seed: one int64 CUDA element')
+        args.seed, args.seed_dev = 0, seed.data_ptr()
+    else:
+        args.seed, args.seed_dev = int(seed) & 0xFFFFFFFF, None
 
 
 def last_forward_kernel() -> str:

@@ -119,6 +119,10 @@ __host__ __device__ __forceinline__ uint32_t dropout_key(uint32_t seed, uint32_t
     return fmix32(a ^ (step * 0x85EBCA6Bu + 0x27D4EB2Fu));
 }
 
+// dropout seed of a call: by value, or -- for calls captured in a CUDA graph, whose arguments are frozen -- from device memory
+template <typename Params>
+__device__ __forceinline__ uint32_t call_seed(const Params& p) { return p.seed_dev ? __ldg(p.seed_dev) : p.seed; }
+
 // keep decision of element idx = row * width + col
 __device__ __forceinline__ bool dropout_keep(uint32_t key, uint64_t idx, float rate) {
     uint32_t lo = (uint32_t)idx, hi = (uint32_t)(idx >> 32);

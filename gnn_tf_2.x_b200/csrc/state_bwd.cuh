@@ -35,6 +35,7 @@ struct BwdNodeParams {
     const int* k_ptr;
     int t;
     uint32_t seed;
+    const uint32_t* seed_dev;   // when set, the dropout seed of the call is read from device memory (CUDA-graph replays)
     int training;
     int row_scale_mode;      // fold cst[:, C] into GA
     // training-mode BatchNormalization
@@ -117,7 +118,7 @@ static __global__ void __launch_bounds__(NT) state_bwd_node_kernel(const BwdNode
     for (int i = tid; i < net.fwd_floats; i += NT) sG[i] = 0.f;
 
     const bool drop_in = p.training && net.drop[0] > 0.f;
-    const uint32_t key_in = dropout_key(p.seed, 0u, (uint32_t)p.t);
+    const uint32_t key_in = dropout_key(call_seed(p), 0u, (uint32_t)p.t);
     const float scale_in = drop_in ? 1.f / (1.f - net.drop[0]) : 1.f;
     const int F_in = net.in_dim[0];
     const float* aff_a = sW + net.aff_off;
@@ -208,7 +209,7 @@ static __global__ void __launch_bounds__(NT) state_bwd_node_kernel(const BwdNode
             const int act = net.act[l], odim = net.out_dim[l];
             const float rate = net.drop[l + 1];
             const bool drop_here = p.training && rate > 0.f;
-            const uint32_t key = dropout_key(p.seed, (uint32_t)(l + 1), (uint32_t)p.t);
+            const uint32_t key = dropout_key(call_seed(p), (uint32_t)(l + 1), (uint32_t)p.t);
             const float dscale = drop_here ? 1.f / (1.f - rate) : 1.f;
             auto epi = [&](int ng, int cg, float (&acc)[8][4]) {
                 const float4 b4 = ld4(bias + 4 * cg);
@@ -237,7 +238,7 @@ static __global__ void __launch_bounds__(NT) state_bwd_node_kernel(const BwdNode
             const int act = net.act[l], odim = net.out_dim[l];
             const float rate = net.drop[L];
             const bool drop_here = p.training && rate > 0.f;
-            const uint32_t key = dropout_key(p.seed, (uint32_t)L, (uint32_t)p.t);
+            const uint32_t key = dropout_key(call_seed(p), (uint32_t)L, (uint32_t)p.t);
             const float dscale = drop_here ? 1.f / (1.f - rate) : 1.f;
             for (int item = tid; item < TN * LPN; item += NT) {
                 const int i = item / LPN, lig = item % LPN;
@@ -277,7 +278,7 @@ static __global__ void __launch_bounds__(NT) state_bwd_node_kernel(const BwdNode
                 const int act = net.act[l - 1], idim = net.in_dim[l];
                 const float rate = net.drop[l];
                 const bool drop_here = p.training && rate > 0.f;
-                const uint32_t key = dropout_key(p.seed, (uint32_t)l, (uint32_t)p.t);
+                const uint32_t key = dropout_key(call_seed(p), (uint32_t)l, (uint32_t)p.t);
                 const float dscale = drop_here ? 1.f / (1.f - rate) : 1.f;
                 auto epi = [&](int ng, int cg, float (&acc)[8][4]) {
 #pragma unroll

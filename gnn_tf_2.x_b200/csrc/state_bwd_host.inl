@@ -80,7 +80,7 @@ extern "C" int gnn_state_loop_backward(const gnn_graph* g, const gnn_mlp* net, c
     GNN_LAUNCH_CHECK();
 
     p.N = N; p.G = w.G; p.cst = w.cst; p.wpack = w.wpack; p.GS = w.GS; p.GA = w.GA; p.gcst = want_cst ? w.gcst : nullptr;
-    p.gpartial = w.gpartial; p.k_ptr = kptr; p.seed = a->seed; p.training = a->training;
+    p.gpartial = w.gpartial; p.k_ptr = kptr; p.seed = a->seed; p.seed_dev = a->seed_dev; p.training = a->training;
     p.row_scale_mode = has_val ? 0 : 1; p.bn_eps = net->bn_eps; p.net = lay; p.has_dB = need_dB ? 1 : 0;
     ScatterKernel scatter = ks->scatter[has_val ? 1 : 0];
     BnBwdReduceKernel bn_reduce = ks->bn_bwd_reduce;

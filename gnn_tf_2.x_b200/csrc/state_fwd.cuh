@@ -46,6 +46,7 @@ struct IterParams {
     double* bn_partial;      // [gridDim.x][2][DP] when bn_train
     int bn_train;
     uint32_t seed;
+    const uint32_t* seed_dev;   // when set, the dropout seed of the call is read from device memory (CUDA-graph replays)
     int training;
     int scol_cap;
     int ring_slots, slot_rows;   // warp-specialised kernel: landing ring = ring_slots x slot_rows state rows
@@ -251,7 +252,7 @@ __global__ void __launch_bounds__(NT, GNN_FWD_MIN_CTAS) state_iter_kernel(const 
 
     const int grp = tid / LPN, lig = tid % LPN;
     const bool drop_in = p.training && net.drop[0] > 0.f;
-    const uint32_t key_in = dropout_key(p.seed, 0u, (uint32_t)p.t);
+    const uint32_t key_in = dropout_key(call_seed(p), 0u, (uint32_t)p.t);
     const float scale_in = drop_in ? 1.f / (1.f - net.drop[0]) : 1.f;
     const int F_in = net.in_dim[0];
 
@@ -343,7 +344,7 @@ __global__ void __launch_bounds__(NT, GNN_FWD_MIN_CTAS) state_iter_kernel(const 
             const int HP = net.out_pad[l], act = net.act[l], odim = net.out_dim[l];
             const float rate = net.drop[l + 1];
             const bool drop_here = p.training && rate > 0.f;
-            const uint32_t key = dropout_key(p.seed, (uint32_t)(l + 1), (uint32_t)p.t);
+            const uint32_t key = dropout_key(call_seed(p), (uint32_t)(l + 1), (uint32_t)p.t);
             const float dscale = drop_here ? 1.f / (1.f - rate) : 1.f;
             float* out;
             int out_stride;

@@ -1,0 +1,560 @@
+// state_fwd_tc.cuh -- the fused forward iteration kernel with the Dense layer on the 5th-generation tensor cores
+// (tcgen05.mma, operands in TENSOR MEMORY) -- the kernel of the headline shape.
+//
+// Why (measured, profiles/r2_*): the warp-level tensor-core path (mma.sync m16n8k8 TF32, SASS HMMA.1688.F32.TF32) that round 1
+// used for the fp32-accurate 3xTF32 Dense layer runs at ~32 pipe cycles per instruction on sm_100a; the 108 of them per 16 nodes
+// kept the legacy HMMA sub-pipe 85 % busy and bounded the iteration at ~0.13 ms BEFORE any gather (state_fwd_ws.cuh).  One
+// tcgen05.mma of shape M=128, N=DP, K=8 does the work of 32 of those instructions on the real tensor pipe; the contraction of
+// a 128-node tile (27 instructions, one issuing thread) disappears from the critical path.
+//
+// One persistent CTA per SM, 14 warps, five roles (register budgets re-split with setmaxnreg):
+//   loader warp  (1): bulk async copies (cp.async.bulk) of row pointers / per-node scales / arc sources of each 64-node staging
+//                     tile, three tiles ahead (a CTA owns a contiguous range of tiles: every copy is one contiguous block).
+//   issue warps  (4): warp c lands sub-tile c (16 nodes) of every staging tile: per 4 source rows one index load from shared
+//                     memory, one address multiply-add, one 16-byte cp.async per lane, into a ring of 8 / 16 slots; completion
+//                     on the slot's mbarrier LANDED (cp.async.mbarrier.arrive.noinc).  They never wait for data.
+//   compute warps (8 = 2 quads): quad g takes the 128-node tiles g, g+2, ...; warp q of the quad owns nodes 32q..32q+31 of the
+//                     tile = TMEM lanes 32q..32q+31, ONE THREAD PER NODE from the staging of the operands on:
+//                       1. own state row + constant row straight from global memory (256-bit loads, one 32-byte sector each),
+//                       2. wait LANDED -> segment sums of its 2 sub-tiles out of the ring in stored order (8 lanes per row,
+//                          packed add.f32x2, deterministic, no atomics) -> warp-private scratch -> slots released at once,
+//                       3. transposition through the scratch (XOR-swizzled: conflict-free both ways): thread = node,
+//                       4. hi / lo split (hi = tf32 part, lo = exact remainder) of [x | agg | cst] -> tcgen05.st into the quad's
+//                          A operand in tensor memory (144 columns), mbarrier A_FULL,
+//                       5. wait D_FULL -> tcgen05.ld of the node's DP accumulators -> bias / activation / affine -> 256-bit
+//                          stores of the new state (+ NVLink peer stores) + convergence test against the own row still in
+//                          registers (+ BatchNormalization batch statistics when training).
+//   MMA warp     (1): one thread: wait A_FULL -> 27 x tcgen05.mma.kind::tf32 (A from tensor memory, B = weights in shared
+//                     memory, canonical K-major layout, pre-split hi / lo): D = A_hi B_hi + A_lo B_hi + A_hi B_lo ->
+//                     tcgen05.commit -> mbarrier D_FULL.
+// Tensor memory: per quad [D (DP) | A_hi (2 DP + 8 CS) | A_lo (same)] = 176 -> 192 columns at DP = 32; 512 allocated.
+//
+// Used for single-Dense-layer state nets (what the reference builds by default) with padded state width 16 or 32, a constant
+// row of at most 16 floats, uniform row weights ('sum' / 'average' / 'normalized' aggregation) and no active dropout; every
+// other case runs state_fwd_ws.cuh or the symmetric kernel.
+#pragma once
+#include "state_fwd_ws.cuh"
+
+namespace gnn {
+
+constexpr int TC_TILE = 128;                 // nodes per tcgen05 tile (M)
+constexpr int TC_QUADS = 2;
+constexpr int TC_COMPUTE = 128 * TC_QUADS;   // warps 0-7
+constexpr int TC_ISSUE = 128;                // warps 8-11
+constexpr int TC_SUM = 128;                  // warps 12-15
+constexpr int TC_LOADER = 32;                // warp 16
+constexpr int TC_MMA = 32;                   // warp 17
+constexpr int TC_IDLE = 64;                  // warps 18-19: give their registers back and wait at the final barrier
+constexpr int TC_THREADS = TC_COMPUTE + TC_ISSUE + TC_SUM + TC_LOADER + TC_MMA + TC_IDLE;   // 640 = 20 warps = 5 per SM sub-partition, 96 registers at launch
+constexpr int TC_REGS_LAUNCH = 96, TC_REGS_COMPUTE = 144, TC_REGS_SUM = 64, TC_REGS_ISSUE = 48, TC_REGS_SMALL = 40, TC_REGS_IDLE = 24;
+// The register file is PHYSICALLY split over the 4 SM sub-partitions (warp w lives on sub-partition w % 4): setmaxnreg.inc can only
+// draw on registers released on its own sub-partition.  Every sub-partition holds 2 compute + 1 issue + 1 sum + 1 loader / MMA / idle
+// warp and was given 5 x 96 registers per lane at launch (an 18-warp launch leaves two sub-partitions with 4 x 96 = 384 < 400: the
+// compute warps there never get their registers and the kernel hangs -- measured the hard way)
+static_assert(TC_THREADS / 32 % 4 == 0, "the same number of warps on every sub-partition");
+static_assert(2 * TC_REGS_COMPUTE + TC_REGS_SUM + TC_REGS_ISSUE + TC_REGS_SMALL <= (TC_THREADS / 128) * TC_REGS_LAUNCH, "registers per lane of one SM sub-partition");
+constexpr int TC_AGGQ = 16;                  // aggregate FIFO: sub-tiles (16 rows each) between the sum warps and the compute warps
+constexpr int TC_TMEM_COLS = 512;
+constexpr int TC_ROWQ = 8, TC_COLQ = 3;      // staging buffers (64-node tiles), as in state_fwd_ws.cuh
+constexpr int TC_SLOTS = 16;
+
+#ifndef GNN_TC_SLEEP
+#define GNN_TC_SLEEP 32
+#endif
+
+// ---- tcgen05 / tensor-memory PTX -------------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, int ncols) {     // one full warp
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, int ncols) {        // the same warp
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem descriptor]; M = 128, K = 8 (tf32)
+__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// thread i of the warp <-> TMEM lane (lane field of taddr) + i; N consecutive 32-bit columns
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// shared-memory matrix descriptor of a K-major operand without swizzle (UMMA "INTERLEAVE"): core matrices of 8 rows x 16 bytes
+// (128 contiguous bytes); lbo = byte distance between the two 16-byte K pieces of one K = 8 step, sbo = byte distance between
+// 8-row blocks.  Fields in units of 16 bytes; bits [46,48) = 1 (sm_100 descriptor version)
+__device__ __forceinline__ uint64_t tc_smem_desc(const void* ptr, int lbo_bytes, int sbo_bytes) {
+    uint64_t d = (uint64_t)((smem_u32(ptr) & 0x3ffffu) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
+    d |= 1ull << 46;
+    return d;
+}
+// instruction descriptor: D fp32, A / B tf32, both K-major, M = 128, N
+__host__ __device__ constexpr uint32_t tc_idesc_tf32(int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+__device__ __forceinline__ void ldg8(const float* p, float (&v)[8]) {      // one 32-byte sector
+    asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "l"(p));
+}
+__device__ __forceinline__ void stg8(float* p, const float (&v)[8]) {
+    asm volatile("st.global.L1::no_allocate.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+}
+
+// v[j] of lane l = value (row l, column j).  After the call v[0] of lane l holds the sum over all 32 rows of column l % W
+// (butterfly: every step halves the values a lane keeps and exchanges the other half with the lane `w` away)
+template <int W>
+__device__ __forceinline__ void warp_column_sums(float (&v)[W], int lane) {
+#pragma unroll
+    for (int w = W / 2; w >= 1; w >>= 1) {
+        const bool upper = (lane & w) != 0;
+#pragma unroll
+        for (int i = 0; i < w; ++i) {
+            const float send = upper ? v[i] : v[i + w];
+            const float keep = upper ? v[i + w] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, w);
+        }
+    }
+#pragma unroll
+    for (int w = W; w < 32; w <<= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], w);     // W < 32: lanes l, l + W hold halves of a column
+}
+
+// k-steps (8 inputs each): own state (DP / 8), aggregated state (DP / 8), constant row (CP / 8, CP padded to 8)
+static inline int tc_ksteps(const NetLayout& lay) { return 2 * (lay.DP / 8) + (lay.CP + 7) / 8; }
+// B operand: per k-step [2 K pieces][DP / 8 row blocks][8 rows][4 floats] = DP * 8 floats, hi and lo copies; + bias, affine a / c
+static inline size_t tc_weight_floats(const NetLayout& lay) { return (size_t)tc_ksteps(lay) * lay.DP * 8 * 2 + 3 * (size_t)lay.DP; }
+static inline size_t tc_smem_bytes(const NetLayout& lay, int ring, int capc, bool bn_train) {
+    size_t fl = tc_weight_floats(lay) + (size_t)TC_AGGQ * WS_SUB * lay.DP + (size_t)ring * lay.DP + TC_ROWQ * 68 + TC_ROWQ * WS_TN +
+                TC_COLQ * (size_t)(capc + WS_COLPAD) + (bn_train ? (size_t)(TC_COMPUTE / 32) * 2 * lay.DP * 2 : 0);
+    return fl * 4;   // weights, aggregate FIFO (16 sub-tiles), ring, row pointers / scales, arc sources, BN sums (fp64)
+}
+
+template <int DP>
+__global__ void __launch_bounds__(TC_THREADS, 1) state_iter_tc_kernel(const IterParams p) {
+    constexpr int TN = WS_TN, LPN = DP / 4;      // 64-node staging tiles, 16-node sub-tiles (as state_fwd_ws.cuh)
+    constexpr int GPW = 32 / LPN;                // source rows per warp-wide cp.async / lane groups per warp
+    constexpr int NPG = WS_SUB / GPW;            // nodes per lane group in the segment-sum phase
+    constexpr int KX = DP / 8;                   // k-steps of a state row
+    static_assert(DP == 16 || DP == 32, "padded state width");
+
+    if (*reinterpret_cast<const volatile int*>(p.go_cur) == 0) return;
+
+    const NetLayout& net = p.net;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int CP = net.CP, capc = p.scol_cap, capb = capc + WS_COLPAD;
+    const int CS = (CP + 7) / 8, KSTEPS = 2 * KX + CS, KA = 8 * KSTEPS;      // A columns per copy (hi or lo)
+    const int nslot = p.ring_slots, slotcap = p.slot_rows;
+
+    extern __shared__ __align__(128) float smem[];
+    float* sBhi = smem;                                  // [KSTEPS][2][DP / 8][8][4]
+    float* sBlo = sBhi + (size_t)KSTEPS * DP * 8;
+    float* sBias = sBlo + (size_t)KSTEPS * DP * 8;       // [DP]
+    float* sAff = sBias + DP;                            // a[DP], c[DP]
+    float* agg0 = sAff + 2 * DP;                         // [TC_AGGQ][16][DP]: aggregated states, 16-byte pieces XOR-swizzled by the row
+    float* land0 = agg0 + TC_AGGQ * WS_SUB * DP;         // [nslot][slotcap][DP]
+    int* srow0 = reinterpret_cast<int*>(land0 + (size_t)nslot * slotcap * DP);   // [TC_ROWQ][68]
+    float* sscale0 = reinterpret_cast<float*>(srow0 + TC_ROWQ * 68);             // [TC_ROWQ][TN]
+    int* scol0 = reinterpret_cast<int*>(sscale0 + TC_ROWQ * TN);                 // [TC_COLQ][capb]
+    double* bn_acc = reinterpret_cast<double*>(scol0 + TC_COLQ * capb);          // [8][2][DP] (training-mode BatchNormalization)
+    __shared__ int s_flag;
+    __shared__ uint32_t s_tmem;
+    __shared__ __align__(8) uint64_t bar_landed[TC_SLOTS], bar_free[TC_SLOTS], bar_cols[TC_COLQ], bar_colfree[TC_COLQ], bar_rows[TC_ROWQ], bar_rowfree[TC_ROWQ],
+        bar_aggfull[TC_AGGQ], bar_aggfree[TC_AGGQ], bar_afull[TC_QUADS], bar_dfull[TC_QUADS];
+
+    // B operand: element (n, k) of k-step ks at [ks][k / 4 (piece)][n / 8][n % 8][k % 4]; K order = [x | agg | cst]
+    for (int i = tid; i < KSTEPS * DP * 8; i += TC_THREADS) {
+        const int e = i & 3, r8 = (i >> 2) & 7, nb = (i >> 5) % (DP / 8), kc = ((i >> 5) / (DP / 8)) & 1, ks = (i >> 5) / (DP / 8) / 2;
+        const int n = 8 * nb + r8, k = 8 * ks + 4 * kc + e;
+        int row;    // input row of the packed Dense kernel [state(DP) | agg(DP) | cst(CP)]
+        if (k < DP) row = k;
+        else if (k < 2 * DP) row = k;
+        else row = (k - 2 * DP) < CP ? k : -1;
+        const float w = row >= 0 ? __ldg(p.wpack + net.w_off[0] + row * DP + n) : 0.f;
+        const float hi = __uint_as_float(__float_as_uint(w) & 0xffffe000u);
+        sBhi[i] = hi;
+        sBlo[i] = w - hi;
+    }
+    for (int i = tid; i < DP; i += TC_THREADS) {
+        sBias[i] = __ldg(p.wpack + net.b_off[0] + i);
+        sAff[i] = __ldg(p.wpack + net.aff_off + i);
+        sAff[DP + i] = __ldg(p.wpack + net.aff_off + DP + i);
+    }
+    if (p.bn_train)
+        for (int i = tid; i < (TC_COMPUTE / 32) * 2 * DP; i += TC_THREADS) bn_acc[i] = 0.;
+    if (tid == 0) {
+        s_flag = 0;
+        for (int i = 0; i < TC_SLOTS; ++i) { mbar_init(&bar_landed[i], 32); mbar_init(&bar_free[i], 1); }
+        for (int i = 0; i < TC_COLQ; ++i) { mbar_init(&bar_cols[i], 1); mbar_init(&bar_colfree[i], WS_NSUB); }
+        for (int i = 0; i < TC_ROWQ; ++i) { mbar_init(&bar_rows[i], 1); mbar_init(&bar_rowfree[i], 2 * WS_NSUB); }   // 4 issue + 4 sum warps
+        for (int i = 0; i < TC_AGGQ; ++i) { mbar_init(&bar_aggfull[i], 1); mbar_init(&bar_aggfree[i], 1); }
+        for (int i = 0; i < TC_QUADS; ++i) { mbar_init(&bar_afull[i], 4); mbar_init(&bar_dfull[i], 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) tmem_alloc(&s_tmem, TC_TMEM_COLS);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // the B operand written above is read by the tensor core (async proxy)
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&s_tmem);
+
+    // this CTA's staging tiles (64 nodes): a contiguous range; compute tiles (128 nodes) = pairs of staging tiles
+    const long long ntiles = (p.N + TN - 1) / TN;
+    const long long t0 = ntiles * blockIdx.x / gridDim.x;
+    const int ntl = (int)(ntiles * (blockIdx.x + 1) / gridDim.x - t0);
+    const int ntl2 = (ntl + 1) / 2;                       // 128-node tiles (the last one may hold one staging tile only)
+    const int stage_cols = (DP + 2 * KA + 63) & ~63;      // TMEM columns of one quad: D | A_hi | A_lo (D aligned to its own width)
+
+    if (warp >= 18) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TC_REGS_IDLE));     // idle warps: registers back to their sub-partition
+    } else if (warp == 17) {
+        // ============================================== MMA WARP ===============================================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TC_REGS_SMALL));
+        if (lane == 0) {
+            const uint32_t idesc = tc_idesc_tf32(DP);
+            const int kstep_bytes = DP * 8 * 4;           // one k-step of B: 2 pieces x DP / 8 blocks x 128 bytes
+            for (int t = 0; t < ntl2; ++t) {
+                const int quad = t & 1;
+                const uint32_t d = tmem_base + quad * stage_cols, a_hi = d + DP, a_lo = a_hi + KA;
+                mbar_wait<GNN_TC_SLEEP>(&bar_afull[quad], (t >> 1) & 1);
+                tc_fence_after();
+                for (int ks = 0; ks < KSTEPS; ++ks) {
+                    const uint64_t bhi = tc_smem_desc(reinterpret_cast<const char*>(sBhi) + (size_t)ks * kstep_bytes, (DP / 8) * 128, 128);
+                    const uint64_t blo = tc_smem_desc(reinterpret_cast<const char*>(sBlo) + (size_t)ks * kstep_bytes, (DP / 8) * 128, 128);
+                    tc_mma_tf32_ts(d, a_hi + 8 * ks, bhi, idesc, ks > 0);
+                    tc_mma_tf32_ts(d, a_lo + 8 * ks, bhi, idesc, 1);
+                    tc_mma_tf32_ts(d, a_hi + 8 * ks, blo, idesc, 1);
+                }
+                tc_commit(&bar_dfull[quad]);              // arrives once every MMA above has completed (accumulator ready, A free)
+            }
+        }
+    } else if (warp == 16) {
+        // ============================================ LOADER WARP ==============================================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TC_REGS_SMALL));
+        const long long E = p.E;
+        auto fetch_bounds = [&](int base) {
+            return base + lane <= ntl ? __ldg(p.rowptr + min((t0 + base + lane) * TN, p.N)) : 0;
+        };
+        int bcur = fetch_bounds(0), bnext = fetch_bounds(32);
+        for (int s = 0; s < ntl; ++s) {
+            const long long n0 = (t0 + s) * TN;
+            const int q8 = s & (TC_ROWQ - 1), q3 = s % TC_COLQ;
+            if ((s & 31) == 0 && s > 0) { bcur = bnext; bnext = fetch_bounds(s + 32); }
+            const int e0 = __shfl_sync(0xffffffffu, bcur, s & 31);
+            const int e1 = (s & 31) == 31 ? __shfl_sync(0xffffffffu, bnext, 0) : __shfl_sync(0xffffffffu, bcur, (s + 1) & 31);
+            const int e0a = e0 & ~3;
+            const int narc = min(e1 - e0a, capb - 4), narc4 = (narc + 3) & ~3;
+            const bool arcs_safe = (long long)e0a + narc4 <= E;
+            const bool rows_safe = n0 + 68 <= p.N + 1 && n0 + TN <= p.N;
+            if (s >= TC_ROWQ) mbar_wait<64>(&bar_rowfree[q8], ((s / TC_ROWQ) - 1) & 1);
+            int* srow = srow0 + q8 * 68;
+            float* ssc = sscale0 + q8 * TN;
+            if (rows_safe) {
+                if (lane == 0) {
+                    mbar_expect_tx(&bar_rows[q8], 68 * 4 + TN * 4);
+                    bulk_copy_g2s(srow, p.rowptr + n0, 68 * 4, &bar_rows[q8]);
+                    bulk_copy_g2s(ssc, p.row_scale + n0, TN * 4, &bar_rows[q8]);
+                }
+            } else {   // last tile of the graph: element-wise, nothing is read past the end of an array
+                for (int i = lane; i <= TN; i += 32) srow[i] = __ldg(p.rowptr + min(n0 + i, p.N));
+                for (int i = lane; i < TN; i += 32) ssc[i] = n0 + i < p.N ? __ldg(p.row_scale + n0 + i) : 0.f;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_rows[q8]);
+            }
+            if (s >= TC_COLQ) mbar_wait<64>(&bar_colfree[q3], ((s / TC_COLQ) - 1) & 1);
+            int* sc = scol0 + (size_t)q3 * capb;
+            if (arcs_safe) {
+                if (lane == 0) {
+                    mbar_expect_tx(&bar_cols[q3], narc4 * 4);
+                    if (narc4 > 0) bulk_copy_g2s(sc, p.col + e0a, narc4 * 4, &bar_cols[q3]);
+                }
+            } else {
+                for (int i = lane; i < narc; i += 32) sc[i] = __ldg(p.col + e0a + i);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_cols[q3]);
+            }
+        }
+    } else if (warp >= 8 && warp < 12) {
+        // ============================================ ISSUE WARPS ==============================================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TC_REGS_ISSUE));
+        const int c = warp - 8;                                 // my sub-tile of every staging tile
+        const int grp = lane / LPN, lig = lane % LPN;
+        const unsigned landed_u32 = smem_u32(bar_landed), free_u32 = smem_u32(bar_free);
+        const float* xl = p.x_in + 4 * lig;
+        const int slot_shift = nslot == 8 ? 3 : 4;
+        for (int s = 0; s < ntl; ++s) {
+            const int q8 = s & (TC_ROWQ - 1), q3 = s % TC_COLQ;
+            mbar_wait(&bar_rows[q8], (s / TC_ROWQ) & 1);
+            mbar_wait(&bar_cols[q3], (s / TC_COLQ) & 1);
+            const int* srow = srow0 + q8 * 68;
+            const int eb = srow[0];
+            const int a0 = srow[WS_SUB * c] - eb;
+            const int cnt = max(0, min(min(srow[WS_SUB * c + WS_SUB] - eb, capc) - a0, slotcap));
+            const int j = WS_NSUB * s + c, slot = j & (nslot - 1);
+            if (j >= nslot) mbar_wait_u32(free_u32 + 8 * slot, ((j >> slot_shift) - 1) & 1);
+            const int* si = scol0 + (size_t)q3 * capb + (eb & 3) + a0;
+            const unsigned lb = smem_u32(land0 + (size_t)slot * slotcap * DP + 4 * lig);
+            if (!(p.ws_debug & 1)) {
+                int r = grp;
+                for (; r + 7 * GPW < cnt; r += 8 * GPW) {
+                    int src[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) src[k] = si[r + k * GPW];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(lb + (unsigned)(r + k * GPW) * (DP * 4)), "l"(xl + (size_t)src[k] * DP));
+                }
+                for (; r < cnt; r += GPW) {
+                    const int src = si[r];
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(lb + (unsigned)r * (DP * 4)), "l"(xl + (size_t)src * DP));
+                }
+            }
+            cp_async_mbar_arrive_u32(landed_u32 + 8 * slot);
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(&bar_colfree[q3]); mbar_arrive(&bar_rowfree[q8]); }
+        }
+        cp_async_wait_group<0>();
+    } else if (warp >= 12) {
+        // ============================================= SUM WARPS ===============================================
+        // warp c drains sub-tile c of every staging tile the moment it has landed: segment sums in stored order (8 lanes per row,
+        // packed add.f32x2, deterministic) -> 16 aggregate rows (2 KB) in the aggregate FIFO -> the 20 KB slot goes straight back
+        // to the issue warp.  The FIFO is 16 sub-tiles deep, so a busy compute quad never holds up the ring.
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TC_REGS_SUM));
+        const int c = warp - 12;
+        const int grpw = lane / LPN, lig = lane % LPN;
+        const int slot_shift = nslot == 8 ? 3 : 4;
+        const uint64_t stream_pol = l2_policy_evict_first();
+        constexpr int SWZ = LPN - 1;
+        for (int s = 0; s < ntl; ++s) {
+            const int q8 = s & (TC_ROWQ - 1);
+            const int j = WS_NSUB * s + c, slot = j & (nslot - 1), phase = (j >> slot_shift) & 1;
+            const int e = j & (TC_AGGQ - 1);
+            const long long n0 = (t0 + s) * TN;
+            const int* srow = srow0 + q8 * 68;
+            mbar_wait<GNN_TC_SLEEP>(&bar_rows[q8], (s / TC_ROWQ) & 1);
+            mbar_wait<GNN_TC_SLEEP>(&bar_landed[slot], phase);
+            if (j >= TC_AGGQ) mbar_wait<GNN_TC_SLEEP>(&bar_aggfree[e], ((j / TC_AGGQ) - 1) & 1);   // the compute warp has read this FIFO entry's previous rows
+            const int ebase = srow[0];
+            const int a0 = srow[WS_SUB * c] - ebase;
+            const int cnt = max(0, min(min(srow[WS_SUB * c + WS_SUB] - ebase, capc) - a0, slotcap));
+            const float* lb = land0 + ((size_t)slot * slotcap - a0) * DP + 4 * lig;
+            float* out = agg0 + (size_t)e * WS_SUB * DP;
+#pragma unroll 1
+            for (int u = 0; u < ((p.ws_debug & 2) ? 0 : NPG); ++u) {
+                const int il = grpw * NPG + u, i = WS_SUB * c + il;     // node of the sub-tile / of the staging tile
+                const int r0 = srow[i] - ebase, r1 = srow[i + 1] - ebase;
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                int r = r0;
+                const int rl = min(r1, a0 + cnt);
+#pragma unroll 4
+                for (; r < rl; ++r) acc = add4_x2(acc, ld4(lb + (ptrdiff_t)r * DP));
+                for (; r < r1; ++r) {   // arcs that did not get ring rows: direct loads (rare, very dense sub-tiles)
+                    const int sidx = __ldg(p.col + ebase + r);
+                    acc = add4(acc, ldg4(p.x_in + (size_t)sidx * DP + 4 * lig));
+                }
+                const float sc = sscale0[q8 * TN + i];
+                acc.x *= sc; acc.y *= sc; acc.z *= sc; acc.w *= sc;
+                if (p.agg_save && n0 + i < p.N) st4_hint(p.agg_save + (size_t)(n0 + i) * DP + 4 * lig, acc, stream_pol);
+                st4(out + il * DP + 4 * (lig ^ (il & SWZ)), acc);
+            }
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&bar_free[slot]);
+                mbar_arrive(&bar_rowfree[q8]);
+                mbar_arrive(&bar_aggfull[e]);
+            }
+        }
+    } else {
+        // =========================================== COMPUTE WARPS =============================================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(TC_REGS_COMPUTE));
+        const int quad = warp >> 2, q = warp & 3;             // q = TMEM lane quarter = nodes 32 q .. 32 q + 31 of the tile
+        const int act = net.act[0], D = net.D;
+        const bool affine = !p.bn_train;
+        bool any_moving = false;
+        double* bn_mine = bn_acc + (size_t)warp * 2 * DP;
+        const uint32_t lane_base = (uint32_t)(32 * q) << 16;  // TMEM address: lane in bits [31:16], column in [15:0]
+        const uint32_t d_acc = tmem_base + quad * stage_cols + lane_base, a_hi = d_acc + DP, a_lo = a_hi + KA;
+        constexpr int SWZ = LPN - 1;                          // pieces per row - 1
+
+        for (int t = quad; t < ntl2; t += TC_QUADS) {
+            const int s = 2 * t + (q >> 1);                   // my staging tile; my sub-tiles c0, c0 + 1
+            const int c0 = 2 * (q & 1);
+            const bool have = s < ntl;                        // the last 128-node tile may end after its first staging tile
+            const long long n0 = (t0 + s) * TN;               // first node of my staging tile
+            const long long node = n0 + 16 * c0 + lane;       // MY node (thread = node from the operand staging on)
+            const bool valid = have && node < p.N;
+            const int q8 = s & (TC_ROWQ - 1);
+
+            // 1. own state row and constant row: 32-byte sectors straight from global memory, in flight during the segment sums
+            float xo[DP], co[16];
+#pragma unroll
+            for (int i = 0; i < DP / 8; ++i) {
+                float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                if (valid) ldg8(p.x_in + (size_t)(p.row_offset + node) * DP + 8 * i, v);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) xo[8 * i + e] = v[e];
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float4 v = (valid && 4 * i < CP) ? ldg4(p.cst + (size_t)node * CP + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                co[4 * i] = v.x; co[4 * i + 1] = v.y; co[4 * i + 2] = v.z; co[4 * i + 3] = v.w;
+            }
+
+            // 2. my 32 aggregate rows = FIFO entries of sub-tiles j0, j0 + 1 (written by sum warps c0, c0 + 1)
+            const int j0 = WS_NSUB * s + c0, e0 = j0 & (TC_AGGQ - 1);
+            if (have) {
+                mbar_wait<GNN_TC_SLEEP>(&bar_aggfull[e0], (j0 / TC_AGGQ) & 1);
+                mbar_wait<GNN_TC_SLEEP>(&bar_aggfull[e0 + 1], (j0 / TC_AGGQ) & 1);
+            }
+
+            // 3. + 4. thread = node: aggregate row out of the scratch, hi / lo split of [x | agg | cst] -> tensor memory
+            //    (the quad's previous tile is complete: its D_FULL was awaited by this very warp before its epilogue)
+            {
+                uint32_t hi[8], lo[8];
+                auto split8 = [&](const float* v) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) { hi[e] = __float_as_uint(v[e]) & 0xffffe000u; lo[e] = __float_as_uint(v[e] - __uint_as_float(hi[e])); }
+                };
+#pragma unroll
+                for (int i = 0; i < KX; ++i) {                 // own state: columns [0, DP)
+                    split8(xo + 8 * i);
+                    tmem_st8(a_hi + 8 * i, hi); tmem_st8(a_lo + 8 * i, lo);
+                }
+#pragma unroll
+                for (int i = 0; i < KX; ++i) {                 // aggregated state: columns [DP, 2 DP)
+                    float v[8];
+                    const float* arow = agg0 + ((size_t)e0 * WS_SUB + lane) * DP;      // entries e0, e0 + 1 are adjacent: row `lane` of the pair
+                    const float4 g0 = ld4(arow + 4 * ((2 * i) ^ (lane & SWZ))), g1 = ld4(arow + 4 * ((2 * i + 1) ^ (lane & SWZ)));
+                    v[0] = g0.x; v[1] = g0.y; v[2] = g0.z; v[3] = g0.w; v[4] = g1.x; v[5] = g1.y; v[6] = g1.z; v[7] = g1.w;
+                    if (!have) {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) v[e] = 0.f;
+                    }
+                    split8(v);
+                    tmem_st8(a_hi + DP + 8 * i, hi); tmem_st8(a_lo + DP + 8 * i, lo);
+                }
+#pragma unroll
+                for (int i = 0; i < 2; ++i)                    // constant row: columns [2 DP, 2 DP + 8 CS)
+                    if (i < CS) {
+                        split8(co + 8 * i);
+                        tmem_st8(a_hi + 2 * DP + 8 * i, hi); tmem_st8(a_lo + 2 * DP + 8 * i, lo);
+                    }
+            }
+            tmem_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if (have) { mbar_arrive(&bar_aggfree[e0]); mbar_arrive(&bar_aggfree[e0 + 1]); }     // FIFO entries back to the sum warps
+                mbar_arrive(&bar_afull[quad]);
+            }
+
+            // 5. epilogue: my node's DP accumulators -> bias / activation / affine -> store + convergence test
+            mbar_wait<GNN_TC_SLEEP>(&bar_dfull[quad], (t >> 1) & 1);
+            tc_fence_after();
+            float y[DP];
+#pragma unroll
+            for (int i = 0; i < DP / 8; ++i) {
+                uint32_t v[8];
+                tmem_ld8(d_acc + 8 * i, v);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) y[8 * i + e] = __uint_as_float(v[e]);
+            }
+            tmem_wait_ld();
+            tc_fence_before();       // orders these loads before the next tile's tcgen05.st / mma (through A_FULL)
+            auto epilogue = [&](auto act_c) {
+                constexpr int ACT = decltype(act_c)::value;
+#pragma unroll
+                for (int jj = 0; jj < DP; ++jj) y[jj] = act_apply(ACT, y[jj] + sBias[jj]);
+                if (affine) {
+#pragma unroll
+                    for (int jj = 0; jj < DP; ++jj) y[jj] = fmaf(sAff[jj], y[jj], sAff[DP + jj]);
+                }
+#pragma unroll
+                for (int jj = 0; jj < DP; ++jj) if (jj >= D) y[jj] = 0.f;       // padding columns stay zero
+            };
+            switch (act) {
+                case GNN_ACT_RELU: epilogue(std::integral_constant<int, GNN_ACT_RELU>{}); break;
+                case GNN_ACT_TANH: epilogue(std::integral_constant<int, GNN_ACT_TANH>{}); break;
+                case GNN_ACT_SIGMOID: epilogue(std::integral_constant<int, GNN_ACT_SIGMOID>{}); break;
+                case GNN_ACT_SELU: epilogue(std::integral_constant<int, GNN_ACT_SELU>{}); break;
+                case GNN_ACT_ELU: epilogue(std::integral_constant<int, GNN_ACT_ELU>{}); break;
+                case GNN_ACT_SOFTPLUS: epilogue(std::integral_constant<int, GNN_ACT_SOFTPLUS>{}); break;
+                default: epilogue(std::integral_constant<int, GNN_ACT_LINEAR>{}); break;
+            }
+            if (valid) {
+                float* orow = p.x_out + (size_t)(p.row_offset + node) * DP;
+#pragma unroll
+                for (int i = 0; i < DP / 8; ++i) {
+                    float v[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) v[e] = y[8 * i + e];
+                    stg8(orow + 8 * i, v);
+                    if (p.n_peers > 1) {
+                        store_to_peers(p, node - 0, 8 * i, make_float4(v[0], v[1], v[2], v[3]));
+                        store_to_peers(p, node - 0, 8 * i + 4, make_float4(v[4], v[5], v[6], v[7]));
+                    }
+                }
+            }
+            if (p.bn_train) {
+                // column sums over my warp's 32 nodes (thread = node): butterfly transpose-reduce, 31 + 31 shuffles; lane j ends
+                // with the totals of column j, accumulated in fp64 in the warp's private row
+                float s1[DP], s2[DP];
+#pragma unroll
+                for (int jj = 0; jj < DP; ++jj) { s1[jj] = valid ? y[jj] : 0.f; s2[jj] = s1[jj] * s1[jj]; }
+                warp_column_sums<DP>(s1, lane);
+                warp_column_sums<DP>(s2, lane);
+                if (lane < DP) {
+                    bn_mine[lane] += (double)s1[0];
+                    bn_mine[DP + lane] += (double)s2[0];
+                }
+            } else {
+                float d2 = 0.f, o2 = 0.f;
+#pragma unroll
+                for (int jj = 0; jj < DP; ++jj) {
+                    const float dx = y[jj] - xo[jj];
+                    d2 = fmaf(dx, dx, d2);
+                    o2 = fmaf(xo[jj], xo[jj], o2);
+                }
+                any_moving |= valid && (sqrtf(d2) > p.thr * sqrtf(o2));
+            }
+        }
+
+        if (p.bn_train) {
+            named_bar_sync(GNN_BAR_MLP_ALL, TC_COMPUTE);
+            if (tid < 2 * DP) {
+                double sum = 0.;
+                for (int w = 0; w < TC_COMPUTE / 32; ++w) sum += bn_acc[(size_t)w * 2 * DP + tid];
+                p.bn_partial[(size_t)blockIdx.x * 2 * DP + tid] = sum;
+            }
+        } else {
+            if (p.go_next && __any_sync(0xffffffffu, any_moving) && lane == 0) s_flag = 1;
+            if (p.n_peers > 1) __threadfence_system();
+            named_bar_sync(GNN_BAR_MLP_ALL, TC_COMPUTE);
+            if (tid == 0) {
+                if (p.go_next && s_flag) atomicOr(p.go_next, 1);
+                if (blockIdx.x == 0) *p.k_ptr = p.t + 1;
+            }
+        }
+        tc_fence_before();
+    }
+    // tensor memory goes back once every role is done with it
+    __syncthreads();
+    if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_base, TC_TMEM_COLS); }
+}
+
+}  // namespace gnn

@@ -5,6 +5,7 @@
 #include "state_bwd.cuh"
 #include "state_fwd.cuh"
 #include "state_fwd_ws.cuh"
+#include "state_fwd_tc.cuh"
 
 namespace gnn {
 
@@ -17,6 +18,7 @@ typedef void (*BnBwdReduceKernel)(const int*, int, const float*, const float*, c
 struct KernelSet {
     IterKernel iter[2][2];      // [tile: 0 = 128 nodes x 128 threads, 1 = 32 x 32][has_val]
     IterKernel iter_ws[2];      // warp-specialised pipeline [has_val]; NULL when the width is not covered
+    IterKernel iter_tc;         // tcgen05 / tensor-memory pipeline (row-scale graphs); NULL when the width is not covered
     BwdNodeKernel bwd_node[2];  // [tile: 0 = 64 nodes x 128 threads, 1 = 32 x 32]
     ScatterKernel scatter[2];   // [has_val]
     BnApplyKernel bn_apply;

@@ -167,7 +167,8 @@ int check_args(const gnn_graph* g, const gnn_mlp* net, const gnn_loop_args* a) {
 }
 
 struct Plan {
-    bool ws;          // warp-specialised pipelined kernel
+    bool ws;          // warp-specialised pipelined kernel (state_fwd_ws.cuh / state_fwd_tc.cuh)
+    bool tc;          // ... its tcgen05 / tensor-memory variant
     NetLayout lay;
     TileShape ts;
     IterKernel kernel;
@@ -178,17 +179,17 @@ struct Plan {
     bool has_val;
 };
 
-// the warp-specialised kernel covers: one Dense layer, padded state width 16..32, no active dropout, enough tiles
+// the warp-specialised kernels cover: one Dense layer, padded state width 16..32, no active dropout, enough tiles
 bool ws_applicable(const gnn_graph* g, const gnn_loop_args* a, const NetLayout& lay, int sms) {
     const char* env = getenv("GNN_B200_KERNEL");
     if (env && !strcmp(env, "sym")) return false;
-    if (lay.L != 1 || lay.DP < 16 || lay.DP > 32 || lay.CP > 16) return false;   // (constant row: at most two k-steps in registers)
+    if (lay.L != 1 || lay.DP < 16 || lay.DP > 32 || lay.CP > 16) return false;   // (constant row: at most two k-steps)
     // the loader warp stages row pointers / arc sources / scales with bulk copies: 16-byte aligned arrays
     auto misaligned = [](const void* ptr) { return ptr && ((uintptr_t)ptr & 15) != 0; };
     if (misaligned(g->rowptr) || misaligned(g->col) || misaligned(g->val) || misaligned(g->row_scale)) return false;
     if (a->training)
         for (int i = 0; i <= lay.L; ++i) if (lay.drop[i] > 0.f) return false;
-    if (env && !strcmp(env, "ws")) return true;
+    if (env && (!strcmp(env, "ws") || !strcmp(env, "tc"))) return true;
     return (g->n_nodes + WS_TN - 1) / WS_TN >= 2LL * sms;
 }
 
@@ -201,18 +202,24 @@ int make_plan(const gnn_graph* g, const gnn_mlp* net, const gnn_loop_args* a, Pl
     plan->has_val = g->val != nullptr && g->row_scale == nullptr;
     const KernelSet* ks = kernel_set(lay.DP);
     if (!ks) GNN_FAIL(GNN_ERR_UNSUPPORTED, "no kernel for padded state width %d", lay.DP);
-    plan->ws = false;
+    plan->ws = plan->tc = false;
     plan->ring_slots = plan->slot_rows = 0;
 
     if (ws_applicable(g, a, lay, di.sms) && ks->iter_ws[plan->has_val ? 1 : 0]) {
+        // tcgen05 variant: graphs with one weight per row ('sum' / 'average' / 'normalized' aggregation); GNN_B200_KERNEL=ws keeps the
+        // mma.sync pipeline (comparison runs)
+        const char* env = getenv("GNN_B200_KERNEL");
+        const bool tc = !plan->has_val && ks->iter_tc && !(env && !strcmp(env, "ws"));
+        const bool bn_tr = a->training && lay.has_bn;
         // arc-index capacity per tile: 1.5x the average tile; the landing ring takes all the shared memory that is left
         // (at least 4 average sub-tiles, at most 4096 rows)
         const long long avg = g->n_nodes > 0 ? (g->n_arcs * WS_TN) / g->n_nodes : 0;
         long long capc_want = avg * 3 / 2;
         if (g->max_block16_arcs > 0) capc_want = std::min<long long>(capc_want, (long long)WS_NSUB * g->max_block16_arcs);   // no tile has more
         const int capc = (int)std::min<long long>(4096, std::max<long long>(128, (capc_want + 15) / 16 * 16));
-        const size_t budget = (size_t)di.smem_optin - 7168;   // static shared memory of the kernel (mbarriers, BN accumulators) + slack
-        const size_t fixed = ws_smem_bytes(lay, 0, capc, plan->has_val);
+        // static shared memory: ws = mbarriers + BN accumulators (4.6 KB), tc = mbarriers only
+        const size_t budget = (size_t)di.smem_optin - (tc ? 1024 : 7168);
+        const size_t fixed = tc ? tc_smem_bytes(lay, 0, capc, bn_tr) : ws_smem_bytes(lay, 0, capc, plan->has_val);
         const int ring = fixed < budget ? (int)std::min<size_t>(4096, (budget - fixed) / ((size_t)lay.DP * 4)) : 0;
         // slots of the ring: one sub-tile (16 nodes) each.  When the caller knows the densest block of 16 rows the slot
         // holds exactly that (bounded by 1.5x the average: hubs read their excess arcs directly); otherwise 1/8 above the
@@ -221,22 +228,23 @@ int make_plan(const gnn_graph* g, const gnn_mlp* net, const gnn_loop_args* a, Pl
         long long want = g->max_block16_arcs > 0 ? std::min<long long>(g->max_block16_arcs, std::max<long long>(32, avg_sub * 3 / 2))
                                                  : avg_sub * 9 / 8;
         const int slot_rows = (int)((want + 3) / 4 * 4);
-        // 8 or 16 slots (a slot then always serves the same consume warp and the same issue group); when not even 8 average
-        // sub-tiles fit, the slots shrink and the consume warps read the excess arcs directly
+        // 8 or 16 slots (a slot then always serves the same issue warp); when not even 8 average sub-tiles fit, the slots shrink
+        // and the compute warps read the excess arcs directly
         int slot_rows_fit = slot_rows;
         int slots = ring / slot_rows >= 16 ? 16 : 8;
         if (ring / slot_rows < 8) slot_rows_fit = (ring / 8) & ~3;
         if (slot_rows_fit < 16 || slot_rows_fit * 2 < avg_sub) slots = 0;
         if (slots >= 8) {
             plan->ws = true;
-            plan->kernel = ks->iter_ws[plan->has_val ? 1 : 0];
-            plan->ts = TileShape{WS_TN, WS_THREADS};
+            plan->tc = tc;
+            plan->kernel = tc ? ks->iter_tc : ks->iter_ws[plan->has_val ? 1 : 0];
+            plan->ts = TileShape{WS_TN, tc ? TC_THREADS : WS_THREADS};
             plan->scol_cap = capc;
             plan->ring_slots = slots;
             plan->slot_rows = slot_rows_fit;
-            plan->smem = ws_smem_bytes(lay, slots * slot_rows_fit, capc, plan->has_val);
+            plan->smem = tc ? tc_smem_bytes(lay, slots * slot_rows_fit, capc, bn_tr) : ws_smem_bytes(lay, slots * slot_rows_fit, capc, plan->has_val);
             int occ = 0;
-            GNN_TRY(kernel_occupancy((const void*)plan->kernel, WS_THREADS, plan->smem, &occ));
+            GNN_TRY(kernel_occupancy((const void*)plan->kernel, plan->ts.nt, plan->smem, &occ));
             const long long ntiles = (g->n_nodes + WS_TN - 1) / WS_TN;
             plan->grid = (int)std::max<long long>(1, std::min<long long>(ntiles, (long long)occ * di.sms));
             return GNN_OK;
@@ -335,13 +343,14 @@ extern "C" int gnn_state_loop_forward(const gnn_graph* g, const gnn_mlp* net, co
     p.rowptr = g->rowptr; p.col = g->col; p.val = plan.has_val ? g->val : nullptr; p.row_scale = plan.has_val ? nullptr : g->row_scale;
     p.N = N; p.E = g->n_arcs; p.row_offset = a->row_offset;
     p.cst = w.cst; p.wpack = w.wpack; p.k_ptr = kptr; p.thr = a->threshold; p.bn_partial = w.bn_partial;
-    p.bn_train = bn_train; p.seed = a->seed; p.training = a->training; p.scol_cap = plan.scol_cap; p.ring_slots = plan.ring_slots; p.slot_rows = plan.slot_rows;
+    p.bn_train = bn_train; p.seed = a->seed; p.seed_dev = a->seed_dev; p.training = a->training; p.scol_cap = plan.scol_cap; p.ring_slots = plan.ring_slots; p.slot_rows = plan.slot_rows;
     { const char* dbg = getenv("GNN_B200_WS_DEBUG"); p.ws_debug = dbg ? atoi(dbg) : 0; } p.net = lay;
     p.n_peers = a->n_global > 0 ? a->n_peers : 0; p.rank = a->rank; p.peer_mask = a->peer_mask;
     BnApplyKernel bn_apply = kernel_set(lay.DP)->bn_apply;
 
-    snprintf(g_last_kernel, sizeof(g_last_kernel), plan.ws ? "state_iter_ws_kernel<%d,%s>" : "state_iter_kernel<%d,%s,%d,%d>", lay.DP,
-             plan.has_val ? "true" : "false", plan.ts.tn, plan.ts.nt);
+    if (plan.tc) snprintf(g_last_kernel, sizeof(g_last_kernel), "state_iter_tc_kernel<%d>", lay.DP);
+    else snprintf(g_last_kernel, sizeof(g_last_kernel), plan.ws ? "state_iter_ws_kernel<%d,%s>" : "state_iter_kernel<%d,%s,%d,%d>", lay.DP,
+                  plan.has_val ? "true" : "false", plan.ts.tn, plan.ts.nt);
     if (g_profile.enabled) {
         GNN_CUDA(cudaEventRecord(g_profile.begin, stream));
         g_profile.launches = 0;

@@ -82,11 +82,19 @@ def _fmix32_t(x: torch.Tensor) -> torch.Tensor:
     return x
 
 
-def dropout_keep_mask(seed: int, stream: int, step: int, rows: int, cols: int, rate: float, device=None,
+def dropout_key_t(seed: torch.Tensor, stream: int, step: int) -> torch.Tensor:
+    """ dropout_key for a seed held on the device (int64 tensor with a value in [0, 2^32)): same arithmetic, torch ops only,
+    so that a CUDA-graph replay draws the mask of the CURRENT seed value """
+    a = _fmix32_t(seed + ((0x9E3779B9 * (stream + 1)) & _M32))
+    return _fmix32_t(a ^ ((step * 0x85EBCA6B + 0x27D4EB2F) & _M32))
+
+
+def dropout_keep_mask(seed, stream: int, step: int, rows: int, cols: int, rate: float, device=None,
                       row_offset: int = 0) -> torch.Tensor:
     """ boolean keep-mask [rows, cols]: element (n, j) is kept iff u(n, j) >= rate, with
-    u = (hash >> 8) * 2**-24 and hash = fmix32(fmix32(lo ^ key) + hi * 0xC2B2AE35 + 0x165667B1), idx = n * cols + j """
-    key = dropout_key(seed, stream, step)
+    u = (hash >> 8) * 2**-24 and hash = fmix32(fmix32(lo ^ key) + hi * 0xC2B2AE35 + 0x165667B1), idx = n * cols + j.
+    seed: python int, or an int64 device tensor (device-side seed of a captured training step) """
+    key = dropout_key_t(seed, stream, step) if isinstance(seed, torch.Tensor) else dropout_key(seed, stream, step)
     n = torch.arange(row_offset, row_offset + rows, dtype=torch.int64, device=device)[:, None]
     j = torch.arange(cols, dtype=torch.int64, device=device)[None, :]
     idx = n * cols + j
@@ -409,6 +417,8 @@ class Adam(Optimizer):
         self.learning_rate, self.beta_1, self.beta_2, self.epsilon = learning_rate, beta_1, beta_2, epsilon
         self.iterations = 0
         self._slots: dict[int, tuple[torch.Tensor, torch.Tensor]] = dict()
+        self.capturable = False            # True: nothing of a step depends on host state (CUDA-graph capture of training_step)
+        self._t_dev: Optional[torch.Tensor] = None
 
     def get_config(self):
         return dict(learning_rate=self.learning_rate, beta_1=self.beta_1, beta_2=self.beta_2, epsilon=self.epsilon)
@@ -416,8 +426,6 @@ class Adam(Optimizer):
     @torch.no_grad()
     def apply_gradients(self, grads_and_vars) -> None:
         self.iterations += 1
-        t = self.iterations
-        lr_t = self.learning_rate * math.sqrt(1.0 - self.beta_2 ** t) / (1.0 - self.beta_1 ** t)
         grads, params, ms, vs = [], [], [], []
         for g, p in grads_and_vars:
             if g is None: continue
@@ -431,7 +439,21 @@ class Adam(Optimizer):
         torch._foreach_addcmul_(vs, grads, grads, value=1.0 - self.beta_2)
         denom = torch._foreach_sqrt(vs)
         torch._foreach_add_(denom, self.epsilon)
-        torch._foreach_addcdiv_(params, ms, denom, value=-lr_t)
+        if self.capturable and params[0].is_cuda:
+            # step counter and bias correction on the device: the same captured CUDA graph serves every replay
+            # (BaseClass.training_step(graph=True)); float64 so that lr_t equals the host formula to the last float32 bit
+            if self._t_dev is None or self._t_dev.device != params[0].device:
+                self._t_dev = torch.full((), float(self.iterations - 1), dtype=torch.float64, device=params[0].device)
+            self._t_dev += 1.0
+            lr_t = self.learning_rate * torch.sqrt(1.0 - self.beta_2 ** self._t_dev) / (1.0 - self.beta_1 ** self._t_dev)
+            step = torch._foreach_div(ms, denom)
+            torch._foreach_mul_(step, lr_t.to(torch.float32))
+            torch._foreach_sub_(params, step)
+        else:
+            t = self.iterations
+            lr_t = self.learning_rate * math.sqrt(1.0 - self.beta_2 ** t) / (1.0 - self.beta_1 ** t)
+            torch._foreach_addcdiv_(params, ms, denom, value=-lr_t)
+            if self._t_dev is not None: self._t_dev.fill_(float(t))
 
 
 class SGD(Optimizer):

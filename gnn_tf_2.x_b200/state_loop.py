@@ -90,7 +90,8 @@ class _StateLoop(torch.autograd.Function):
         args.x0, args.nodes = x0c.data_ptr(), None if nodes_c is None else nodes_c.data_ptr()
         args.agg_nodes, args.agg_arcs = agg_nodes_c.data_ptr(), agg_arcs_c.data_ptr()
         args.max_iter, args.threshold = int(cfg.max_iter), float(cfg.threshold)
-        args.training, args.save_for_backward, args.seed = int(bool(cfg.training)), int(save), int(cfg.seed) & 0xFFFFFFFF
+        args.training, args.save_for_backward = int(bool(cfg.training)), int(save)
+        N.set_seed(args, cfg.seed)
         args.x_out, args.k_out = x_out.data_ptr(), k_out.data_ptr()
 
         if part is not None:
@@ -156,7 +157,8 @@ class _StateLoop(torch.autograd.Function):
         args.x0, args.nodes = x0c.data_ptr(), None if nodes_c is None else nodes_c.data_ptr()
         args.agg_nodes, args.agg_arcs = agg_nodes_c.data_ptr(), agg_arcs_c.data_ptr()
         args.max_iter, args.threshold = int(cfg.max_iter), float(cfg.threshold)
-        args.training, args.save_for_backward, args.seed = int(bool(cfg.training)), 1, int(cfg.seed) & 0xFFFFFFFF
+        args.training, args.save_for_backward = int(bool(cfg.training)), 1
+        N.set_seed(args, cfg.seed)
         args.x_out = args.k_out = None        # not touched by the backward sweep
 
         # gradients of the trainable variables, Keras order: [kernel, bias] per Dense (+ gamma, beta)
@@ -215,7 +217,8 @@ def state_loop(adjacency: SparseCSR, net_state: Sequential, x0: torch.Tensor, no
     cfg.D = int(x0.shape[1])
     cfg.NL_self = 0 if nodes is None else int(nodes.shape[1])
     cfg.NL_agg, cfg.AL = int(aggregated_nodes.shape[1]), int(aggregated_arcs.shape[1])
-    cfg.max_iter, cfg.threshold, cfg.training, cfg.seed = int(max_iteration), float(threshold), bool(training), int(seed)
+    cfg.max_iter, cfg.threshold, cfg.training = int(max_iteration), float(threshold), bool(training)
+    cfg.seed = seed if isinstance(seed, torch.Tensor) else int(seed)     # device tensor: seed read at kernel time (captured steps)
     cfg.partition = partition
     if cfg.spec.dims[0] != 2 * cfg.D + cfg.NL_self + cfg.NL_agg + cfg.AL:
         raise ValueError(f'net_state input width {cfg.spec.dims[0]} does not match the graph: expected '

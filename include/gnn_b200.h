@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define GNN_B200_ABI_VERSION 3
+#define GNN_B200_ABI_VERSION 4
 #define GNN_MAX_LAYERS 4 /* Dense layers per MLP */
 #define GNN_MAX_PEERS 8  /* GPUs of one NVSwitch domain */
 
@@ -171,6 +171,10 @@ typedef struct gnn_loop_args {
     int32_t rank;
     float* peer_state[GNN_MAX_PEERS];
     const uint32_t* peer_mask;
+    /* Optional: device [1].  When non-NULL the dropout generator takes the seed of the call from device memory at kernel
+     * time instead of `seed`: a forward / backward pair captured in a CUDA graph (arguments frozen at capture) then draws
+     * new masks at every replay as long as the caller advances the value between replays. */
+    const uint32_t* seed_dev;
 } gnn_loop_args;
 
 int gnn_state_loop_workspace_bytes(const gnn_graph* g, const gnn_mlp* net, const gnn_loop_args* a, size_t* bytes);

@@ -162,6 +162,44 @@ def test_train_reduces_loss_and_keeps_history_keys():
     assert gnn.history['Epoch'][-1] == 30
 
 
+@pytest.mark.parametrize('problem', ['n', 'g'])
+def test_cuda_graph_training_step_equals_eager(problem):
+    """ use_cuda_graph: the whole training step captured once per batch graph and replayed (while_loop launches, BPTT sweep,
+    output net, Adam).  Dropout masks and the Adam step counter must advance at every replay exactly as in eager mode:
+    after 4 epochs over 3 batches the weights of a graphed model equal those of an eager twin """
+    _require_gpu()
+    from gnn_b200 import GNN_utils as utils
+    from gnn_b200.MLP import MLP, get_inout_dims
+    from gnn_b200.GNN import GNNnodeBased, GNNgraphBased
+    from gnn_b200.graph_class import GraphTensor
+    from gnn_b200.keras_compat import Adam, categorical_crossentropy
+    graphs = _toy_dataset(problem, n_graphs=18, seed=9)
+    batches = [GraphTensor.fromGraphObject(b) for b in utils.getbatches(graphs, problem, 'average', batch_size=6)]
+
+    def make():
+        f_s, l_s = get_inout_dims('state', 3, 1, 2, problem, 0, None)
+        f_o, l_o = get_inout_dims('output', 3, 1, 2, problem, 0, None)
+        net_s = MLP(f_s, l_s, 'selu', 'lecun_normal', 'lecun_normal', dropout_rate=0.1, dropout_pos=0, batch_normalization=True, seed=3)
+        net_o = MLP(f_o, l_o, 'softmax', 'glorot_normal', 'glorot_normal', dropout_rate=0.1, dropout_pos=0, batch_normalization=False, seed=4)
+        cls = {'n': GNNnodeBased, 'g': GNNgraphBased}[problem]
+        return cls(net_s, net_o, Adam(learning_rate=0.01), categorical_crossentropy, {'from_logits': False}, state_vect_dim=0, max_iteration=5,
+                   threshold=0.01, addressed_problem='c', path_writer='/tmp/gnn_b200_graphed/')
+
+    eager, graphed = make(), make()
+    graphed.use_cuda_graph = True
+    losses = {id(eager): [], id(graphed): []}
+    for epoch in range(4):
+        for b in batches:
+            for m in (eager, graphed):
+                iters, loss = m.training_step(b)
+                losses[id(m)].append((float(iters[0]), float(loss)))
+    assert any(entry[0] == 'graph' for b in batches for entry in b.__dict__['_step_graphs'].values())
+    for (k1, l1), (k2, l2) in zip(losses[id(eager)], losses[id(graphed)]):
+        assert k1 == k2 and abs(l1 - l2) <= 1e-5 * max(1.0, abs(l1)), (k1, l1, k2, l2)
+    for w1, w2 in zip(eager.net_state.get_weights() + eager.net_output.get_weights(), graphed.net_state.get_weights() + graphed.net_output.get_weights()):
+        np.testing.assert_allclose(w2, w1, rtol=2e-5, atol=2e-6)
+
+
 def test_training_step_matches_keras_adam_on_oracle_gradients():
     """ one optimizer step == Keras-Adam formula applied to the oracle's (gradient / k) """
     _require_gpu()

@@ -344,10 +344,13 @@ WS_CASES = {
 }
 
 
+@pytest.mark.parametrize('kernel', ['tc', 'ws'])
 @pytest.mark.parametrize('name', sorted(WS_CASES))
-def test_ws_kernel_forward_and_training(name, monkeypatch):
+def test_ws_kernel_forward_and_training(name, kernel, monkeypatch):
+    """ both pipelined kernels forced on small cases: 'tc' = tcgen05 / tensor-memory Dense layer (state_fwd_tc.cuh; per-arc weights
+    fall through to the mma.sync pipeline), 'ws' = mma.sync pipeline (state_fwd_ws.cuh) """
     _require_gpu()
-    monkeypatch.setenv('GNN_B200_KERNEL', 'ws')
+    monkeypatch.setenv('GNN_B200_KERNEL', kernel)
     case = random_case(seed=700 + sorted(WS_CASES).index(name), **WS_CASES[name])
     assert_parity(run_cuda(case, training=False), run_oracle(case, training=False))
     got, want = run_cuda(case, training=True), run_oracle(case, training=True)
@@ -366,8 +369,10 @@ def test_ws_and_symmetric_kernels_agree(monkeypatch):
     b = run_cuda(case, training=False)
     assert _native.last_forward_kernel().startswith('state_iter_kernel<32,false')
     monkeypatch.delenv('GNN_B200_KERNEL')
-    c = run_cuda(case, training=False)      # the planner's own choice at this size: the warp-specialised kernel, bit-identical
-    assert _native.last_forward_kernel() == 'state_iter_ws_kernel<32,false>'
-    np.testing.assert_array_equal(a['state'], c['state'])
-    assert a['k'] == b['k']
+    c = run_cuda(case, training=False)      # the planner's own choice at this size: the tcgen05 pipeline
+    assert _native.last_forward_kernel() == 'state_iter_tc_kernel<32>'
+    c2 = run_cuda(case, training=False)
+    np.testing.assert_array_equal(c['state'], c2['state'])      # deterministic
+    assert a['k'] == b['k'] == c['k']
     assert rel_err(a["state"], b["state"]) < 2e-5   # 3xTF32 tensor-core product vs sequential fp32 FMA
+    assert rel_err(c["state"], b["state"]) < 2e-5   # same, tcgen05

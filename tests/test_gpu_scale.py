@@ -40,12 +40,12 @@ def _c4(name):
 
 @pytest.mark.parametrize('name', ['c4u', 'c4l'])
 def test_c4_full_size_forward_and_training_parity(name):
-    """ the timed configuration itself: 1M nodes / 10M arcs / D = 32 -> the warp-specialised kernel with the ring sized for this graph """
+    """ the timed configuration itself: 1M nodes / 10M arcs / D = 32 -> the tcgen05 pipeline with the ring sized for this graph """
     _require_gpu()
     from gnn_b200 import _native
     bench, wl, gnn, gt = _c4(name)
     res = bench.parity_check(wl, gnn, gt, torch.device('cuda'), 2, training=False)
-    assert _native.last_forward_kernel() == 'state_iter_ws_kernel<32,false>'
+    assert _native.last_forward_kernel() == 'state_iter_tc_kernel<32>'
     assert res['k_equal'] and res['k'] == 2.0
     assert res['max_rel'] <= TOL, res
     assert res['elementwise_rel_p99'] <= TOL, res
