@@ -140,7 +140,7 @@ def bench_graph_batches(args, device, rank, world):
             iters, _ = gnn.training_step(gt)
             ks.append(iters[0])
 
-    for _ in range(max(3, args.warmup)): epoch()     # (CUDA graph: two eager steps + the capture of every batch happen here)
+    for _ in range(max(3, args.warmup)): epoch()     # (CUDA graph: the eager first step and the capture of every batch happen here)
     torch.cuda.synchronize()
     if world > 1: dist.barrier()
     _native.launch_count(reset=True)
@@ -400,7 +400,7 @@ def bench_small(args, device):
                     iters, _ = model.training_step(gt)
                     ks.append(iters)
 
-            for _ in range(max(3, args.warmup)): epoch()        # (graphed: two eager steps + the capture happen here)
+            for _ in range(max(3, args.warmup)): epoch()        # (graphed: the eager first step and the capture happen here)
             torch.cuda.synchronize()
             _native.launch_count(reset=True)
             start.record()

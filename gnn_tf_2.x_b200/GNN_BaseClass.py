@@ -162,12 +162,12 @@ class BaseClass(ABC):
             self.optimizer.capturable = True
             for m in self._seeded_models():
                 if getattr(m, '_seed_state', None) is None: m._device_seed(True, g.device)
-            # two eager steps on a side stream first (PyTorch's capture protocol: lazy initialisation, allocator warm-up, optimizer
-            # slots) -- they are real training steps, not discarded work
+            # the first step of a batch graph runs eagerly on a side stream (PyTorch's capture protocol: lazy initialisation,
+            # allocator warm-up, optimizer slots); the second call captures, every later call replays.  One optimizer step per call.
             side = torch.cuda.Stream(device=g.device)
             side.wait_stream(torch.cuda.current_stream(g.device))
             with torch.cuda.stream(side):
-                for _ in range(2): out = self._training_step_eager(g, mean)
+                out = self._training_step_eager(g, mean)
             torch.cuda.current_stream(g.device).wait_stream(side)
             cache[key] = ('warm',)
             return out

@@ -53,6 +53,7 @@ class gnn_loop_args(C.Structure):
                 ('x_out', C.c_void_p), ('k_out', C.c_void_p),
                 ('n_global', C.c_int64), ('row_offset', C.c_int64), ('exchange', C.c_void_p), ('exchange_user', C.c_void_p),
                 ('n_peers', C.c_int32), ('rank', C.c_int32), ('peer_state', C.c_void_p * 8), ('peer_mask', C.c_void_p),
+                ('sig_local', C.c_void_p), ('sig_peer', C.c_void_p * 8), ('sig_epoch', C.c_uint32),
                 ('seed_dev', C.c_void_p)]
 
 

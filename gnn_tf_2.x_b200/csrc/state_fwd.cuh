@@ -31,6 +31,16 @@ struct IterParams {
     int n_peers, rank;       // fused NVLink exchange: new rows are also stored into the peers' state buffers
     float* peer_out[GNN_MAX_PEERS];
     const uint32_t* peer_mask;
+    // in-kernel cross-GPU signalling of the node-range partition (no host-side collective per iteration): every rank owns a signal
+    // area in peer-mapped memory, arrive[sig_iters][8] | flag[sig_iters][8] (int32, slot [t][r] written by rank r): the last CTA of
+    // iteration t stores its rank's convergence flag and then an arrival mark (the call's epoch, release, system scope) into every
+    // peer's area; the CTAs of iteration t+1 wait for all marks, OR the flags and run or stop together
+    int32_t* sig_local;
+    int32_t* sig_peer[GNN_MAX_PEERS];
+    uint32_t sig_epoch;
+    int sig_iters;
+    int* stopped;            // local: set once the loop has stopped, later launches return at once
+    int* done_ctr;           // local: CTAs of this launch that are done (zeroed with the loop control words)
     // state
     const float* x_in;       // [N, DP]
     float* x_out;            // [N, DP]  (pre-BN output h_t when bn_train)
@@ -128,6 +138,59 @@ __device__ __forceinline__ float4 gather_rows(const float* __restrict__ x_in, in
         else acc = add4(acc, r);
     }
     return acc;
+}
+
+__device__ __forceinline__ uint32_t ld_acquire_sys_u32(const void* ptr) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(ptr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys_u32(void* ptr, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(ptr), "r"(v) : "memory");
+}
+
+// Does iteration p.t run?  Uniform over the grid; contains a block-wide barrier (call it before any role split).
+// Single GPU / host-side exchange: the device flag go[t].  In-kernel signalling: wait for every rank's arrival mark of this
+// iteration (written by the last CTA of its previous launch), then OR the ranks' flags.
+__device__ __forceinline__ bool iter_begin(const IterParams& p) {
+    if (p.sig_local == nullptr) return *reinterpret_cast<const volatile int*>(p.go_cur) != 0;
+    __shared__ int s_go;
+    if (threadIdx.x == 0) {
+        int go = 0;
+        if (*reinterpret_cast<const volatile int*>(p.stopped)) go = 0;
+        else if (p.t == 0) go = *reinterpret_cast<const volatile int*>(p.go_cur);     // first test: evaluated on all rows by every rank
+        else
+            for (int r = 0; r < p.n_peers; ++r) {
+                while ((int32_t)(ld_acquire_sys_u32(p.sig_local + (size_t)p.t * 8 + r) - p.sig_epoch) < 0) __nanosleep(40);
+                go |= reinterpret_cast<const volatile int32_t*>(p.sig_local)[(size_t)(p.sig_iters + p.t) * 8 + r];
+            }
+        s_go = go;
+        if (!go && blockIdx.x == 0) *p.stopped = 1;
+    }
+    __syncthreads();
+    return s_go != 0;
+}
+
+// End of a CTA's work on iteration p.t; ONE thread per CTA, after a block-level barrier behind which every thread has made its
+// (peer) stores and executed __threadfence_system().  cta_flag: some node of this CTA still moves.
+__device__ __forceinline__ void iter_end(const IterParams& p, int cta_flag) {
+    if (p.go_next && cta_flag) atomicOr(p.go_next, 1);
+    if (blockIdx.x == 0) *p.k_ptr = p.t + 1;
+    if (p.sig_local == nullptr || p.go_next == nullptr) return;
+    __threadfence_system();
+    if (atomicAdd(p.done_ctr, 1) != (int)gridDim.x - 1) return;
+    // last CTA of this rank: everything this launch stored (locally and into the peers) is ordered before the marks below
+    __threadfence_system();
+    const int flag = atomicOr(p.go_next, 0);
+    for (int r = 0; r < p.n_peers; ++r) {
+        int32_t* area = r == p.rank ? p.sig_local : p.sig_peer[r];
+        reinterpret_cast<volatile int32_t*>(area)[(size_t)(p.sig_iters + p.t + 1) * 8 + p.rank] = flag;
+    }
+    __threadfence_system();
+    for (int r = 0; r < p.n_peers; ++r) {
+        int32_t* area = r == p.rank ? p.sig_local : p.sig_peer[r];
+        st_release_sys_u32(area + (size_t)(p.t + 1) * 8 + p.rank, p.sig_epoch);
+    }
 }
 
 #ifndef GNN_GATHER_BATCH
@@ -231,7 +294,7 @@ __global__ void __launch_bounds__(NT, GNN_FWD_MIN_CTAS) state_iter_kernel(const 
     constexpr int NGRP = NT / LPN;       // node rows gathered concurrently by a CTA
     static_assert(LPN >= 1 && LPN <= 32 && NT % LPN == 0, "lane mapping");
 
-    if (*reinterpret_cast<const volatile int*>(p.go_cur) == 0) return;  // loop already stopped (uniform)
+    if (!iter_begin(p)) return;  // loop already stopped (uniform)
 
     const NetLayout& net = p.net;
     const int tid = threadIdx.x;
@@ -464,11 +527,8 @@ __global__ void __launch_bounds__(NT, GNN_FWD_MIN_CTAS) state_iter_kernel(const 
             for (int c = 0; c < 4; ++c) { dst[4 * tid + c] = s1[c]; dst[DP + 4 * tid + c] = s2[c]; }
         }
     } else {
-        if (p.n_peers > 1) __threadfence_system();   // peer stores performed before the kernel is reported complete
-        if (tid == 0) {
-            if (p.go_next && s_flag) atomicOr(p.go_next, 1);
-            if (blockIdx.x == 0) *p.k_ptr = p.t + 1;
-        }
+        if (p.n_peers > 1) { __threadfence_system(); __syncthreads(); }   // peer stores performed before the kernel is reported complete
+        if (tid == 0) iter_end(p, s_flag);
     }
 }
 

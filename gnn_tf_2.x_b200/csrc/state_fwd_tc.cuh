@@ -7,12 +7,15 @@
 // tcgen05.mma of shape M=128, N=DP, K=8 does the work of 32 of those instructions on the real tensor pipe; the contraction of
 // a 128-node tile (27 instructions, one issuing thread) disappears from the critical path.
 //
-// One persistent CTA per SM, 14 warps, five roles (register budgets re-split with setmaxnreg):
+// One persistent CTA per SM, 24 warps (22 working), six roles (register budgets re-split with setmaxnreg):
 //   loader warp  (1): bulk async copies (cp.async.bulk) of row pointers / per-node scales / arc sources of each 64-node staging
 //                     tile, three tiles ahead (a CTA owns a contiguous range of tiles: every copy is one contiguous block).
 //   issue warps  (4): warp c lands sub-tile c (16 nodes) of every staging tile: per 4 source rows one index load from shared
 //                     memory, one address multiply-add, one 16-byte cp.async per lane, into a ring of 8 / 16 slots; completion
 //                     on the slot's mbarrier LANDED (cp.async.mbarrier.arrive.noinc).  They never wait for data.
+//   sum warps    (8): sub-tile j -> warp j % 8: segment sums out of the ring the moment the rows have landed (8 lanes per row,
+//                     stored order, packed add.f32x2, deterministic) -> 16 aggregate rows in the 16-deep aggregate FIFO; the 20 KB
+//                     slot goes straight back to the issue warp (the ring only saturates the memory system when ALL of it is in flight)
 //   compute warps (8 = 2 quads): quad g takes the 128-node tiles g, g+2, ...; warp q of the quad owns nodes 32q..32q+31 of the
 //                     tile = TMEM lanes 32q..32q+31, ONE THREAD PER NODE from the staging of the operands on:
 //                       1. own state row + constant row straight from global memory (256-bit loads, one 32-byte sector each),
@@ -41,18 +44,18 @@ constexpr int TC_TILE = 128;                 // nodes per tcgen05 tile (M)
 constexpr int TC_QUADS = 2;
 constexpr int TC_COMPUTE = 128 * TC_QUADS;   // warps 0-7
 constexpr int TC_ISSUE = 128;                // warps 8-11
-constexpr int TC_SUM = 128;                  // warps 12-15
-constexpr int TC_LOADER = 32;                // warp 16
-constexpr int TC_MMA = 32;                   // warp 17
-constexpr int TC_IDLE = 64;                  // warps 18-19: give their registers back and wait at the final barrier
-constexpr int TC_THREADS = TC_COMPUTE + TC_ISSUE + TC_SUM + TC_LOADER + TC_MMA + TC_IDLE;   // 640 = 20 warps = 5 per SM sub-partition, 96 registers at launch
-constexpr int TC_REGS_LAUNCH = 96, TC_REGS_COMPUTE = 144, TC_REGS_SUM = 64, TC_REGS_ISSUE = 48, TC_REGS_SMALL = 40, TC_REGS_IDLE = 24;
+constexpr int TC_SUM = 256;                  // warps 12-19
+constexpr int TC_LOADER = 32;                // warp 20
+constexpr int TC_MMA = 32;                   // warp 21
+constexpr int TC_IDLE = 64;                  // warps 22-23: give their registers back and wait at the final barrier
+constexpr int TC_THREADS = TC_COMPUTE + TC_ISSUE + TC_SUM + TC_LOADER + TC_MMA + TC_IDLE;   // 768 = 24 warps = 6 per SM sub-partition, 80 registers at launch
+constexpr int TC_REGS_LAUNCH = 80, TC_REGS_COMPUTE = 128, TC_REGS_SUM = 64, TC_REGS_ISSUE = 48, TC_REGS_SMALL = 40, TC_REGS_IDLE = 24;
 // The register file is PHYSICALLY split over the 4 SM sub-partitions (warp w lives on sub-partition w % 4): setmaxnreg.inc can only
-// draw on registers released on its own sub-partition.  Every sub-partition holds 2 compute + 1 issue + 1 sum + 1 loader / MMA / idle
-// warp and was given 5 x 96 registers per lane at launch (an 18-warp launch leaves two sub-partitions with 4 x 96 = 384 < 400: the
-// compute warps there never get their registers and the kernel hangs -- measured the hard way)
+// draw on registers released on its own sub-partition.  Every sub-partition holds 2 compute + 1 issue + 2 sum + 1 loader / MMA / idle
+// warp and was given 6 x 80 registers per lane at launch (an 18-warp launch left two sub-partitions with 4 x 96 = 384 < 400: the
+// compute warps there never got their registers and the kernel hung -- measured the hard way)
 static_assert(TC_THREADS / 32 % 4 == 0, "the same number of warps on every sub-partition");
-static_assert(2 * TC_REGS_COMPUTE + TC_REGS_SUM + TC_REGS_ISSUE + TC_REGS_SMALL <= (TC_THREADS / 128) * TC_REGS_LAUNCH, "registers per lane of one SM sub-partition");
+static_assert(2 * TC_REGS_COMPUTE + 2 * TC_REGS_SUM + TC_REGS_ISSUE + TC_REGS_SMALL <= (TC_THREADS / 128) * TC_REGS_LAUNCH, "registers per lane of one SM sub-partition");
 constexpr int TC_AGGQ = 16;                  // aggregate FIFO: sub-tiles (16 rows each) between the sum warps and the compute warps
 constexpr int TC_TMEM_COLS = 512;
 constexpr int TC_ROWQ = 8, TC_COLQ = 3;      // staging buffers (64-node tiles), as in state_fwd_ws.cuh
@@ -153,7 +156,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) state_iter_tc_kernel(const Iter
     constexpr int KX = DP / 8;                   // k-steps of a state row
     static_assert(DP == 16 || DP == 32, "padded state width");
 
-    if (*reinterpret_cast<const volatile int*>(p.go_cur) == 0) return;
+    if (!iter_begin(p)) return;
 
     const NetLayout& net = p.net;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -220,9 +223,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) state_iter_tc_kernel(const Iter
     const int ntl2 = (ntl + 1) / 2;                       // 128-node tiles (the last one may hold one staging tile only)
     const int stage_cols = (DP + 2 * KA + 63) & ~63;      // TMEM columns of one quad: D | A_hi | A_lo (D aligned to its own width)
 
-    if (warp >= 18) {
+    if (warp >= 22) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TC_REGS_IDLE));     // idle warps: registers back to their sub-partition
-    } else if (warp == 17) {
+    } else if (warp == 21) {
         // ============================================== MMA WARP ===============================================
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TC_REGS_SMALL));
         if (lane == 0) {
@@ -243,7 +246,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) state_iter_tc_kernel(const Iter
                 tc_commit(&bar_dfull[quad]);              // arrives once every MMA above has completed (accumulator ready, A free)
             }
         }
-    } else if (warp == 16) {
+    } else if (warp == 20) {
         // ============================================ LOADER WARP ==============================================
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TC_REGS_SMALL));
         const long long E = p.E;
@@ -331,16 +334,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) state_iter_tc_kernel(const Iter
         cp_async_wait_group<0>();
     } else if (warp >= 12) {
         // ============================================= SUM WARPS ===============================================
-        // warp c drains sub-tile c of every staging tile the moment it has landed: segment sums in stored order (8 lanes per row,
+        // warp w drains sub-tile w % 4 of the staging tiles of parity w / 4 the moment it has landed: segment sums in stored order (8 lanes per row,
         // packed add.f32x2, deterministic) -> 16 aggregate rows (2 KB) in the aggregate FIFO -> the 20 KB slot goes straight back
         // to the issue warp.  The FIFO is 16 sub-tiles deep, so a busy compute quad never holds up the ring.
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TC_REGS_SUM));
-        const int c = warp - 12;
+        const int c = (warp - 12) & 3;
         const int grpw = lane / LPN, lig = lane % LPN;
         const int slot_shift = nslot == 8 ? 3 : 4;
         const uint64_t stream_pol = l2_policy_evict_first();
         constexpr int SWZ = LPN - 1;
-        for (int s = 0; s < ntl; ++s) {
+        for (int s = (warp - 12) >> 2; s < ntl; s += 2) {
             const int q8 = s & (TC_ROWQ - 1);
             const int j = WS_NSUB * s + c, slot = j & (nslot - 1), phase = (j >> slot_shift) & 1;
             const int e = j & (TC_AGGQ - 1);
@@ -354,23 +357,49 @@ __global__ void __launch_bounds__(TC_THREADS, 1) state_iter_tc_kernel(const Iter
             const int cnt = max(0, min(min(srow[WS_SUB * c + WS_SUB] - ebase, capc) - a0, slotcap));
             const float* lb = land0 + ((size_t)slot * slotcap - a0) * DP + 4 * lig;
             float* out = agg0 + (size_t)e * WS_SUB * DP;
+            if (!(p.ws_debug & 2)) {
+                // the NPG nodes of my lane group side by side: NPG independent accumulation chains (each one sums its rows in stored
+                // order), one row of every node per step -- the shared-memory loads of a step are independent of each other
+                const int i0 = WS_SUB * c + grpw * NPG;          // first node (of the staging tile) of my lane group
+                int rb[NPG + 1];
+#pragma unroll
+                for (int u = 0; u <= NPG; ++u) rb[u] = srow[i0 + u] - ebase;
+                float4 acc[NPG];
+                int len = 0;
+#pragma unroll
+                for (int u = 0; u < NPG; ++u) { acc[u] = make_float4(0.f, 0.f, 0.f, 0.f); len = max(len, min(rb[u + 1], a0 + cnt) - rb[u]); }
+                // two steps at a time: 2 NPG independent 128-bit loads first (the shared-memory pipe is shared with the landing copies,
+                // a load takes ~100 cycles under load), then the adds
+                int rend[NPG];
+#pragma unroll
+                for (int u = 0; u < NPG; ++u) rend[u] = min(rb[u + 1], a0 + cnt);
 #pragma unroll 1
-            for (int u = 0; u < ((p.ws_debug & 2) ? 0 : NPG); ++u) {
-                const int il = grpw * NPG + u, i = WS_SUB * c + il;     // node of the sub-tile / of the staging tile
-                const int r0 = srow[i] - ebase, r1 = srow[i + 1] - ebase;
-                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                int r = r0;
-                const int rl = min(r1, a0 + cnt);
-#pragma unroll 4
-                for (; r < rl; ++r) acc = add4_x2(acc, ld4(lb + (ptrdiff_t)r * DP));
-                for (; r < r1; ++r) {   // arcs that did not get ring rows: direct loads (rare, very dense sub-tiles)
-                    const int sidx = __ldg(p.col + ebase + r);
-                    acc = add4(acc, ldg4(p.x_in + (size_t)sidx * DP + 4 * lig));
+                for (int k = 0; k < len; k += 2) {
+                    float4 v[2][NPG];
+#pragma unroll
+                    for (int kk = 0; kk < 2; ++kk)
+#pragma unroll
+                        for (int u = 0; u < NPG; ++u) {
+                            const int r = rb[u] + k + kk;
+                            v[kk][u] = r < rend[u] ? ld4(lb + (ptrdiff_t)r * DP) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+#pragma unroll
+                    for (int kk = 0; kk < 2; ++kk)
+#pragma unroll
+                        for (int u = 0; u < NPG; ++u) acc[u] = add4_x2(acc[u], v[kk][u]);
                 }
-                const float sc = sscale0[q8 * TN + i];
-                acc.x *= sc; acc.y *= sc; acc.z *= sc; acc.w *= sc;
-                if (p.agg_save && n0 + i < p.N) st4_hint(p.agg_save + (size_t)(n0 + i) * DP + 4 * lig, acc, stream_pol);
-                st4(out + il * DP + 4 * (lig ^ (il & SWZ)), acc);
+#pragma unroll
+                for (int u = 0; u < NPG; ++u) {
+                    const int il = grpw * NPG + u, i = i0 + u;
+                    for (int r = max(rb[u], a0 + cnt); r < rb[u + 1]; ++r) {   // arcs that did not get ring rows: direct loads (rare, very dense sub-tiles)
+                        const int sidx = __ldg(p.col + ebase + r);
+                        acc[u] = add4(acc[u], ldg4(p.x_in + (size_t)sidx * DP + 4 * lig));
+                    }
+                    const float sc = sscale0[q8 * TN + i];
+                    acc[u].x *= sc; acc[u].y *= sc; acc[u].z *= sc; acc[u].w *= sc;
+                    if (p.agg_save && n0 + i < p.N) st4_hint(p.agg_save + (size_t)(n0 + i) * DP + 4 * lig, acc[u], stream_pol);
+                    st4(out + il * DP + 4 * (lig ^ (il & SWZ)), acc[u]);
+                }
             }
             __syncwarp();
             if (lane == 0) {
@@ -391,6 +420,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) state_iter_tc_kernel(const Iter
         const uint32_t d_acc = tmem_base + quad * stage_cols + lane_base, a_hi = d_acc + DP, a_lo = a_hi + KA;
         constexpr int SWZ = LPN - 1;                          // pieces per row - 1
 
+        // own state row + constant row of MY node of a tile: 32-byte sectors straight from global memory, requested ONE TILE AHEAD
+        // (in flight during the staging / MMA / epilogue of the current tile -- nothing waits on their latency)
+        float xn[DP], cn[16];
+        auto prefetch_own = [&](int t) {
+            const int s = 2 * t + (q >> 1);
+            const long long node = (t0 + s) * TN + 32 * (q & 1) + lane;
+            const bool valid = t < ntl2 && s < ntl && node < p.N;
+#pragma unroll
+            for (int i = 0; i < DP / 8; ++i) {
+                float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                if (valid) ldg8(p.x_in + (size_t)(p.row_offset + node) * DP + 8 * i, v);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) xn[8 * i + e] = v[e];
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float4 v = (valid && 4 * i < CP) ? ldg4(p.cst + (size_t)node * CP + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                cn[4 * i] = v.x; cn[4 * i + 1] = v.y; cn[4 * i + 2] = v.z; cn[4 * i + 3] = v.w;
+            }
+        };
+        prefetch_own(quad);
+
         for (int t = quad; t < ntl2; t += TC_QUADS) {
             const int s = 2 * t + (q >> 1);                   // my staging tile; my sub-tiles c0, c0 + 1
             const int c0 = 2 * (q & 1);
@@ -398,22 +449,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) state_iter_tc_kernel(const Iter
             const long long n0 = (t0 + s) * TN;               // first node of my staging tile
             const long long node = n0 + 16 * c0 + lane;       // MY node (thread = node from the operand staging on)
             const bool valid = have && node < p.N;
-            const int q8 = s & (TC_ROWQ - 1);
-
-            // 1. own state row and constant row: 32-byte sectors straight from global memory, in flight during the segment sums
-            float xo[DP], co[16];
-#pragma unroll
-            for (int i = 0; i < DP / 8; ++i) {
-                float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                if (valid) ldg8(p.x_in + (size_t)(p.row_offset + node) * DP + 8 * i, v);
-#pragma unroll
-                for (int e = 0; e < 8; ++e) xo[8 * i + e] = v[e];
-            }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float4 v = (valid && 4 * i < CP) ? ldg4(p.cst + (size_t)node * CP + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
-                co[4 * i] = v.x; co[4 * i + 1] = v.y; co[4 * i + 2] = v.z; co[4 * i + 3] = v.w;
-            }
 
             // 2. my 32 aggregate rows = FIFO entries of sub-tiles j0, j0 + 1 (written by sum warps c0, c0 + 1)
             const int j0 = WS_NSUB * s + c0, e0 = j0 & (TC_AGGQ - 1);
@@ -432,7 +467,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) state_iter_tc_kernel(const Iter
                 };
 #pragma unroll
                 for (int i = 0; i < KX; ++i) {                 // own state: columns [0, DP)
-                    split8(xo + 8 * i);
+                    split8(xn + 8 * i);
                     tmem_st8(a_hi + 8 * i, hi); tmem_st8(a_lo + 8 * i, lo);
                 }
 #pragma unroll
@@ -451,7 +486,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) state_iter_tc_kernel(const Iter
 #pragma unroll
                 for (int i = 0; i < 2; ++i)                    // constant row: columns [2 DP, 2 DP + 8 CS)
                     if (i < CS) {
-                        split8(co + 8 * i);
+                        split8(cn + 8 * i);
                         tmem_st8(a_hi + 2 * DP + 8 * i, hi); tmem_st8(a_lo + 2 * DP + 8 * i, lo);
                     }
             }
@@ -462,6 +497,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) state_iter_tc_kernel(const Iter
                 if (have) { mbar_arrive(&bar_aggfree[e0]); mbar_arrive(&bar_aggfree[e0 + 1]); }     // FIFO entries back to the sum warps
                 mbar_arrive(&bar_afull[quad]);
             }
+            prefetch_own(t + TC_QUADS);        // next tile's rows: in flight while the tensor core works and during the epilogue
 
             // 5. epilogue: my node's DP accumulators -> bias / activation / affine -> store + convergence test
             mbar_wait<GNN_TC_SLEEP>(&bar_dfull[quad], (t >> 1) & 1);
@@ -523,13 +559,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) state_iter_tc_kernel(const Iter
                     bn_mine[DP + lane] += (double)s2[0];
                 }
             } else {
+                // convergence test against the OLD state of my node: hi + lo = the exact fp32 row, still in the A operand (tensor memory)
                 float d2 = 0.f, o2 = 0.f;
 #pragma unroll
-                for (int jj = 0; jj < DP; ++jj) {
-                    const float dx = y[jj] - xo[jj];
-                    d2 = fmaf(dx, dx, d2);
-                    o2 = fmaf(xo[jj], xo[jj], o2);
+                for (int i = 0; i < DP / 8; ++i) {
+                    uint32_t vh[8], vl[8];
+                    tmem_ld8(a_hi + 8 * i, vh);
+                    tmem_ld8(a_lo + 8 * i, vl);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const float xo = __uint_as_float(vh[e]) + __uint_as_float(vl[e]);
+                        const float dx = y[8 * i + e] - xo;
+                        d2 = fmaf(dx, dx, d2);
+                        o2 = fmaf(xo, xo, o2);
+                    }
                 }
+                tc_fence_before();     // these loads precede the next tile's tcgen05.st into the same columns
                 any_moving |= valid && (sqrtf(d2) > p.thr * sqrtf(o2));
             }
         }
@@ -545,10 +591,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) state_iter_tc_kernel(const Iter
             if (p.go_next && __any_sync(0xffffffffu, any_moving) && lane == 0) s_flag = 1;
             if (p.n_peers > 1) __threadfence_system();
             named_bar_sync(GNN_BAR_MLP_ALL, TC_COMPUTE);
-            if (tid == 0) {
-                if (p.go_next && s_flag) atomicOr(p.go_next, 1);
-                if (blockIdx.x == 0) *p.k_ptr = p.t + 1;
-            }
+            if (tid == 0) iter_end(p, s_flag);
         }
         tc_fence_before();
     }

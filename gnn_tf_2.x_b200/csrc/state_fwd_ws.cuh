@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) state_iter_ws_kernel(const Iter
     static_assert(DP % 8 == 0 && TN == 64 && WS_NSUB == 4, "4 MLP warps x 16 nodes, DP / 8 accumulator fragments each");
     static_assert(WS_ISSUE == 32 * WS_NSUB, "one issue warp per sub-tile of a tile");
 
-    if (*reinterpret_cast<const volatile int*>(p.go_cur) == 0) return;
+    if (!iter_begin(p)) return;
 
     const NetLayout& net = p.net;
     const int tid = threadIdx.x;
@@ -626,10 +626,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) state_iter_ws_kernel(const Iter
             if (p.go_next && __any_sync(0xffffffffu, any_moving) && (tid & 31) == 0) s_flag = 1;
             if (p.n_peers > 1) __threadfence_system();   // peer stores performed before the kernel is reported complete
             named_bar_sync(GNN_BAR_MLP_ALL, WS_MLP_ALL);
-            if (tid == 0) {
-                if (p.go_next && s_flag) atomicOr(p.go_next, 1);
-                if (blockIdx.x == 0) *p.k_ptr = p.t + 1;
-            }
+            if (tid == 0) iter_end(p, s_flag);
         }
     }
 }

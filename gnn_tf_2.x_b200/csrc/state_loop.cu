@@ -82,7 +82,7 @@ TileShape pick_tile(long long N, int sms) {
 
 // ---- workspace -----------------------------------------------------------------------------------------
 struct Workspace {
-    int* ctl;          // go[0..max_iter], k
+    int* ctl;          // go[0..max_iter], k, stopped, done[0..max_iter-1]
     float* wpack;
     float* cst;
     float* stats;      // [max_iter][4][DP] BatchNormalization batch statistics per iteration
@@ -119,7 +119,7 @@ int carve(const gnn_graph* g, const gnn_loop_args* a, const NetLayout& lay, void
     w->slab = NG * (size_t)lay.DP;
     w->max_ctas = di.sms * 32;
     w->x_slabs = save ? a->max_iter + 1 : 2;
-    size_t o_ctl = take((size_t)(a->max_iter + 2) * sizeof(int));
+    size_t o_ctl = take((size_t)(2 * a->max_iter + 3) * sizeof(int));
     size_t o_wp = take((size_t)lay.total_floats * 4);
     size_t o_cst = take(N * (size_t)lay.CP * 4);
     size_t o_stats = take(bn_train ? (size_t)a->max_iter * 4 * lay.DP * 4 : 0);
@@ -160,6 +160,9 @@ int check_args(const gnn_graph* g, const gnn_mlp* net, const gnn_loop_args* a) {
         if (a->training || a->save_for_backward) GNN_FAIL(GNN_ERR_UNSUPPORTED, "partitioned calls are forward-only");
         if (a->n_peers < 0 || a->n_peers > GNN_MAX_PEERS) GNN_FAIL(GNN_ERR_INVALID, "n_peers outside 0..%d", GNN_MAX_PEERS);
         if (a->n_peers > 1 && (a->rank < 0 || a->rank >= a->n_peers)) GNN_FAIL(GNN_ERR_INVALID, "rank outside 0..n_peers-1");
+        if (a->sig_local && a->n_peers > 1)
+            for (int r = 0; r < a->n_peers; ++r)
+                if (r != a->rank && !a->sig_peer[r]) GNN_FAIL(GNN_ERR_INVALID, "sig_peer[%d] missing", r);
     } else if (a->row_offset != 0 || a->exchange || a->n_peers > 1) {
         GNN_FAIL(GNN_ERR_INVALID, "row_offset / exchange / peers need n_global");
     }
@@ -316,7 +319,7 @@ extern "C" int gnn_state_loop_forward(const gnn_graph* g, const gnn_mlp* net, co
     int* go = w.ctl;
     int* kptr = w.ctl + a->max_iter + 1;
 
-    GNN_CUDA(cudaMemsetAsync(w.ctl, 0, (size_t)(a->max_iter + 2) * sizeof(int), stream));
+    GNN_CUDA(cudaMemsetAsync(w.ctl, 0, (size_t)(2 * a->max_iter + 3) * sizeof(int), stream));
     {
         PackParams pp;
         pp.net = *net; pp.lay = lay; pp.wpack = w.wpack; pp.state_loop = 1;
@@ -346,6 +349,10 @@ extern "C" int gnn_state_loop_forward(const gnn_graph* g, const gnn_mlp* net, co
     p.bn_train = bn_train; p.seed = a->seed; p.seed_dev = a->seed_dev; p.training = a->training; p.scol_cap = plan.scol_cap; p.ring_slots = plan.ring_slots; p.slot_rows = plan.slot_rows;
     { const char* dbg = getenv("GNN_B200_WS_DEBUG"); p.ws_debug = dbg ? atoi(dbg) : 0; } p.net = lay;
     p.n_peers = a->n_global > 0 ? a->n_peers : 0; p.rank = a->rank; p.peer_mask = a->peer_mask;
+    if (p.n_peers > 1 && a->sig_local) {
+        p.sig_local = a->sig_local; p.sig_epoch = a->sig_epoch; p.sig_iters = a->max_iter + 1; p.stopped = w.ctl + a->max_iter + 2;
+        for (int r = 0; r < p.n_peers; ++r) p.sig_peer[r] = a->sig_peer[r];
+    }
     BnApplyKernel bn_apply = kernel_set(lay.DP)->bn_apply;
 
     if (plan.tc) snprintf(g_last_kernel, sizeof(g_last_kernel), "state_iter_tc_kernel<%d>", lay.DP);
@@ -364,6 +371,7 @@ extern "C" int gnn_state_loop_forward(const gnn_graph* g, const gnn_mlp* net, co
         p.go_cur = go + t;
         p.go_next = (t + 1 < a->max_iter) ? go + t + 1 : nullptr;
         p.t = t;
+        p.done_ctr = w.ctl + a->max_iter + 3 + t;
         for (int r = 0; r < p.n_peers; ++r) p.peer_out[r] = a->peer_state[r] ? a->peer_state[r] + (size_t)((t + 1) & 1) * w.slab : nullptr;
         if (N > 0) {
             void* args[] = {(void*)&p};

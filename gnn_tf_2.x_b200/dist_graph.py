@@ -96,6 +96,7 @@ class HaloPlan:
 
 
 _SYMMETRIC_WORKSPACES: dict = dict()
+_SIGNALS: dict = dict()          # (device, group) -> [symmetric int32 signal area, handle, capacity in iterations, epoch of the last call]
 
 
 class GraphPartition:
@@ -158,10 +159,10 @@ class GraphPartition:
         import os
         env = os.environ.get('GNN_B200_FUSED')                    # '0' / '1': force the NCCL / the fused exchange (experiments)
         if env is not None: fused = env != '0'
-        # measured on 8 x B200 with every row travelling to every peer (uniform sources): NCCL all-gather 14.5 ms per 50 iterations,
-        # fused 16-byte peer stores 16.1 ms (at 2 GPUs the fused path wins 1.6x); boundary-only exchanges stay fused
-        if env is None and self.halo is not None and self.halo.use_allgather and world >= 8: fused = False
+        # round 1 fell back to an NCCL all-gather at 8 ranks when every row travels (14.5 ms per 50 iterations against 16.1 ms for 16-byte
+        # peer stores); with 32-byte row pieces and no per-iteration host collective the fused path is used at every N
         self.fused = bool(fused and world > 1 and world <= 8 and self.device.type == 'cuda')
+        self.in_kernel_signals = self.fused and os.environ.get('GNN_B200_SIGNALS', '1') != '0'     # '0': per-iteration NCCL all-reduce of the flag
         self._ws = self._handle = self._peer_mask = self._state_offsets = None
         self._order = torch.zeros(1, dtype=torch.int32, device=self.device) if world > 1 else None
         if self.fused: self._build_peer_mask()
@@ -200,11 +201,39 @@ class GraphPartition:
         self._ws, self._handle = cached
         return self._ws
 
+    def _signals(self, iters: int):
+        """ the group's signal area for the in-kernel cross-GPU signalling (gnn_loop_args.sig_*): symmetric memory, zero-filled ONCE
+        (marks are epochs that only grow), re-allocated when a loop needs more iterations than it holds """
+        import torch.distributed._symmetric_memory as symm
+        key = (str(self.device), id(self.group))
+        entry = _SIGNALS.get(key)
+        if entry is None or entry[2] < iters:
+            cap = max(64, 2 * iters)
+            sig = symm.empty(2 * 8 * cap, dtype=torch.int32, device=self.device)
+            sig.zero_()
+            handle = symm.rendezvous(sig, group=self.group if self.group is not None else dist.group.WORLD)
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group=self.group)              # every rank's area is zero before anybody signals
+            entry = _SIGNALS[key] = [sig, handle, cap, 0 if entry is None else entry[3]]
+        return entry
+
+    needs_callback = property(lambda self: self.world > 1 and not (self.fused and self.in_kernel_signals))
+
     def peer_setup(self, args, workspace, state_offset: int) -> None:
         if self.world == 1: return
         # order this call after everything the peers did with the shared buffers in the previous call
         dist.all_reduce(self._order, op=dist.ReduceOp.MAX, group=self.group)
         if not self.fused: return
+        if self.in_kernel_signals:
+            try:
+                entry = self._signals(int(args.max_iter) + 1)
+            except Exception as exc:                        # no symmetric memory for the signals: host-side flag reduction
+                self.in_kernel_signals, self._signal_error = False, repr(exc)
+            else:
+                entry[3] += 1                               # one epoch per partitioned call, the same on every rank
+                args.sig_local = int(entry[1].buffer_ptrs[self.rank])
+                for r in range(self.world): args.sig_peer[r] = int(entry[1].buffer_ptrs[r])
+                args.sig_epoch = entry[3] & 0xFFFFFFFF
         # The offset of the state buffers inside the workspace depends on max_iteration, the size of the packed net and the
         # width of the constant rows: another GNN / LGNN layer over the same partition moves it.  The cache is keyed on the
         # local layout; every rank runs the same program (same nets, same max_iteration), so all ranks re-gather together.

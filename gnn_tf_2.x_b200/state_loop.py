@@ -109,7 +109,7 @@ class _StateLoop(torch.autograd.Function):
             N.check(lib.gnn_state_loop_layout(C.byref(graph), C.byref(mlp), C.byref(args), C.byref(off), C.byref(sbytes)),
                     'gnn_state_loop_layout')
             part.peer_setup(args, workspace, int(off.value))      # fills n_peers / rank / peer_state / peer_mask, orders the call
-        if part is not None:
+        if part is not None and getattr(part, 'needs_callback', True):
             DP = 4
             while DP < cfg.D: DP *= 2
             slab_bytes = int(part.n_global) * DP * 4

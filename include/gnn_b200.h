@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define GNN_B200_ABI_VERSION 4
+#define GNN_B200_ABI_VERSION 5
 #define GNN_MAX_LAYERS 4 /* Dense layers per MLP */
 #define GNN_MAX_PEERS 8  /* GPUs of one NVSwitch domain */
 
@@ -171,6 +171,16 @@ typedef struct gnn_loop_args {
     int32_t rank;
     float* peer_state[GNN_MAX_PEERS];
     const uint32_t* peer_mask;
+    /* In-kernel signalling (optional, with the fused exchange): no collective and no callback between the iterations.
+     * sig_local / sig_peer[r] address one signal area per rank in peer-mapped memory (sig_peer[r] = rank r's area as seen from
+     * THIS device; sig_local = this rank's own), each 2 * 8 * (max_iter + 1) int32, zero-filled when allocated and never reset:
+     * arrive[t][r] | flag[t][r].  The last CTA of iteration t on rank r writes its convergence flag and then the call's
+     * sig_epoch (release, system scope) into slot [t + 1][r] of every rank; the CTAs of iteration t + 1 wait until all ranks'
+     * marks have reached sig_epoch (compared modulo 2^32: use a counter that grows with every partitioned call of the group)
+     * and OR the flags, so every rank runs the same iterations.  exchange may then be NULL. */
+    int32_t* sig_local;
+    int32_t* sig_peer[GNN_MAX_PEERS];
+    uint32_t sig_epoch;
     /* Optional: device [1].  When non-NULL the dropout generator takes the seed of the call from device memory at kernel
      * time instead of `seed`: a forward / backward pair captured in a CUDA graph (arguments frozen at capture) then draws
      * new masks at every replay as long as the caller advances the value between replays. */

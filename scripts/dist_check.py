@@ -29,13 +29,31 @@ for name, kw in {'uniform': dict(n_nodes=40000, n_arcs=320000), 'converging': di
         for rep in range(2):      # twice: the second call re-uses the symmetric workspace
             k, x, out = dist_graph.partitioned_loop(gnn, part)
         lo, hi = part.row_offset, part.row_offset + part.n_local
+        signals = getattr(part, 'in_kernel_signals', False)
         # every rank holds its own rows + the rows it gathers from; other remote rows are only valid when all rows travel
         e_state = rel_err(x.cpu().numpy(), x_ref.cpu().numpy()) if part.halo.use_allgather else rel_err(x[lo:hi].cpu().numpy(), x_ref[lo:hi].cpu().numpy())
         e_out = rel_err(out.cpu().numpy(), out_ref[lo:hi].cpu().numpy())
         good = float(k) == float(k_ref) and e_state < 1e-6 and e_out < 1e-6
         ok &= good
-        print(f'[rank {rank}] {name}: requested fused={fused} used fused={part.fused} {getattr(part, "_fused_error", "")} k {float(k)} vs {float(k_ref)}, '
+        print(f'[rank {rank}] {name}: requested fused={fused} used fused={part.fused} in-kernel signals={signals} {getattr(part, "_fused_error", "")} k {float(k)} vs {float(k_ref)}, '
               f'state err {e_state:.2e}, out err {e_out:.2e}, rows {"all" if part.halo.use_allgather else "boundary"} -> {"OK" if good else "FAIL"}', flush=True)
+    # another net (wider constant row, other max_iteration) over the SAME partition object: the state buffers sit at another offset of
+    # the symmetric workspace (the cached peer offsets must follow) and the signal area is re-used with a new epoch
+    case2 = random_case(**dict(base, seed=601, AL=1, max_iter=base['max_iter'] + 3))
+    case2['arcs'] = np.concatenate([case['arcs'][:, :2], case['arcs'][:, 2:3]], axis=1)
+    case2['nodes'], case2['targets'], case2['sample_weights'] = case['nodes'], case['targets'], case['sample_weights']
+    g2, gt2, gnn2 = build_product(case2, device=f'cuda:{local}')
+    with torch.no_grad():
+        k_ref, x_ref, out_ref = gnn2.Loop(gt2, training=False)
+    part2 = dist_graph.GraphPartition(g2, rank, world, device=f'cuda:{local}', fused=True)
+    for which, gg, pp, ref in (('first net again', gnn, part, None), ('second net', gnn2, part2, (k_ref, x_ref, out_ref))):
+        k, x, out = dist_graph.partitioned_loop(gg, pp)
+        if ref is None: continue
+        lo, hi = pp.row_offset, pp.row_offset + pp.n_local
+        e_state = rel_err(x[lo:hi].cpu().numpy(), ref[1][lo:hi].cpu().numpy())
+        good = float(k) == float(ref[0]) and e_state < 1e-6
+        ok &= good
+        print(f'[rank {rank}] {name} / {which}: k {float(k)} vs {float(ref[0])}, state err {e_state:.2e} -> {"OK" if good else "FAIL"}', flush=True)
 flag = torch.tensor([0 if ok else 1], device='cuda')
 dist.all_reduce(flag)
 dist.destroy_process_group()

@@ -147,7 +147,7 @@ gather_ring(const float* __restrict__ x, const __grid_constant__ CUtensorMap tm,
     __shared__ __align__(8) uint64_t landed[SLOTS], freeb[SLOTS], idxb[NI], idxfree[NI];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
-        for (int i = 0; i < SLOTS; ++i) { mb_init(&landed[i], MODE == 0 ? 32 : 1); mb_init(&freeb[i], 1); }
+        for (int i = 0; i < SLOTS; ++i) { mb_init(&landed[i], (MODE == 0 || (MODE == 2 && (i % NIW) % 2 == 0)) ? 32 : 1); mb_init(&freeb[i], 1); }
         for (int i = 0; i < NI; ++i) { mb_init(&idxb[i], 1); mb_init(&idxfree[i], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -171,7 +171,7 @@ gather_ring(const float* __restrict__ x, const __grid_constant__ CUtensorMap tm,
             if (j >= SLOTS) mb_wait(&freeb[slot], ((j / SLOTS) - 1) & 1);
             const int* si = sidx + q * ROWS;
             float* lb = land + (size_t)slot * ROWS * 32;
-            if (MODE == 0) {
+            if (MODE == 0 || (MODE == 2 && (w & 1) == 0)) {
                 const int g = lane >> 3, l8 = lane & 7;
                 const float* xl = x + 4 * l8;
                 float* db = lb + 4 * l8;
@@ -198,7 +198,7 @@ gather_ring(const float* __restrict__ x, const __grid_constant__ CUtensorMap tm,
                 __syncwarp();
             }
         }
-        if (MODE == 0) asm volatile("cp.async.wait_all;" ::: "memory");
+        if (MODE != 1) asm volatile("cp.async.wait_all;" ::: "memory");
     } else {
         const int c = warp - 1 - NIW, g = lane >> 3, l8 = lane & 7;
         for (int j = c; j < cnt; j += NCW) {
@@ -289,10 +289,11 @@ int main(int argc, char** argv) {
 #define RING(MODE, NIW, NCW, SLOTS) { \
             size_t smr = (size_t)SLOTS * 160 * 128 + 2 * SLOTS * 160 * 4; \
             CK(cudaFuncSetAttribute(gather_ring<MODE, NIW, NCW, SLOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smr)); \
-            char nm[128]; snprintf(nm, 128, "%s ring %d slots, %d issue + %d consume warps", MODE ? "D gather4" : "E cp.async", SLOTS, NIW, NCW); \
+            char nm[128]; snprintf(nm, 128, "%s ring %d slots, %d issue + %d consume warps", MODE == 2 ? "F hybrid cp.async / gather4" : MODE ? "D gather4" : "E cp.async", SLOTS, NIW, NCW); \
             CK(cudaMemset(out, 0, N * 128)); \
             TIME(nm, (gather_ring<MODE, NIW, NCW, SLOTS><<<sms, 32 * (1 + NIW + NCW), smr>>>(x, tm, col, n_sub, out))); check(nm); }
         RING(0, 4, 8, 8) RING(0, 2, 8, 8) RING(0, 8, 8, 8) RING(0, 2, 10, 10) RING(0, 4, 4, 8) RING(0, 4, 4, 4)
+        RING(2, 8, 8, 8) RING(2, 4, 8, 8) RING(2, 8, 4, 8)
         RING(1, 4, 8, 8) RING(1, 2, 8, 8) RING(1, 8, 8, 8) RING(1, 1, 8, 8) RING(1, 2, 10, 10)
     }
     // streaming reference: read x once, write out once
