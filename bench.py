@@ -36,6 +36,14 @@ def algorithmic_bytes_per_iteration(N, E, D, NL, AL, per_arc_weights=False):
     return 4 * E * (2 if per_arc_weights else 1) + N * (4 + 8 * D + 4 * (2 * NL + AL))
 
 
+def progress(msg: str) -> None:
+    """ one stderr line per leg (with the rank and the wall clock): a multi-GPU run that stalls shows where """
+    print(f'[bench rank {os.environ.get("RANK", "0")} +{time.perf_counter() - _T0:7.1f}s] {msg}', file=sys.stderr, flush=True)
+
+
+_T0 = time.perf_counter()
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # workload
 # ---------------------------------------------------------------------------------------------------------------------
@@ -115,6 +123,7 @@ def bench_graph_batches(args, device, rank, world):
     from gnn_b200.GNN import GNNgraphBased
     from gnn_b200.keras_compat import Dense, Sequential, Adam, categorical_crossentropy
     total, per_step = args.graphs_total, args.graphs_per_step
+    progress(f'c5: generating the graph batches of rank {rank}')
     n_batches = max(world, total // per_step)
     mine = [b for b in range(n_batches) if b * world // n_batches == rank]          # contiguous blocks of batches per rank
     gts, arcs = [], 0
@@ -140,7 +149,9 @@ def bench_graph_batches(args, device, rank, world):
             iters, _ = gnn.training_step(gt)
             ks.append(iters[0])
 
+    progress(f'c5: {len(gts)} batches on the device, warm-up / capture')
     for _ in range(max(3, args.warmup)): epoch()     # (CUDA graph: the eager first step and the capture of every batch happen here)
+    progress('c5: timed epochs')
     torch.cuda.synchronize()
     if world > 1: dist.barrier()
     _native.launch_count(reset=True)
@@ -523,8 +534,10 @@ def main():
     g_host = GraphObject(arcs=wl['arcs'], nodes=wl['nodes'], targets=wl['targets'], problem_based='n', aggregation_mode='average',
                          _endpoints=(wl['src'], wl['dst']))
     if world > 1:
+        progress(f'{args.workload}: partitioned forward loop + e2e')
         with ClockSampler(local_rank) as clocks:
             result = dist_graph.bench_partitioned(g_host, wl, build_gnn, args, device, rank, world)
+        progress(f'{args.workload}: done, {result["ms_per_step"]:.2f} ms per loop')
         variant = None
         if not args.skip_variant and args.workload in ('c4u', 'c4l'):
             other = 'c4l' if args.workload == 'c4u' else 'c4u'
@@ -533,7 +546,9 @@ def main():
             g2 = GraphObject(arcs=wl2['arcs'], nodes=wl2['nodes'], targets=wl2['targets'], problem_based='n', aggregation_mode='average',
                              _endpoints=(wl2['src'], wl2['dst']))
             wl.update(x0=wl2['x0'], ws=wl2['ws'], wo=wl2['wo'])
+            progress(f'{other}: partitioned forward loop')
             r2 = dist_graph.bench_partitioned(g2, wl2, build_gnn, args, device, rank, world, with_e2e=False)
+            progress(f'{other}: done, {r2["ms_per_step"]:.2f} ms per loop')
             variant = {'workload': other + (': sources within +-2048 of the destination (boundary rows travel)' if other == 'c4l' else ': uniform sources'),
                        'value': r2['value'], 'ms_per_step': r2['ms_per_step'], 'iterations': r2['iterations'], 'partition': r2['partition']}
         batches = None

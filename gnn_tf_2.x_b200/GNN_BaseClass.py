@@ -173,7 +173,8 @@ class BaseClass(ABC):
             return out
         if entry[0] == 'warm':
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
+            # thread_local: other threads (the NCCL watchdog of torch.distributed) may call the CUDA API while this thread captures
+            with torch.cuda.graph(graph, capture_error_mode='thread_local'):
                 iters, loss, dW, flat = self._step_gradients(g, mean)
                 if distributed:
                     packed = torch.cat([d.reshape(-1) for d in dW])

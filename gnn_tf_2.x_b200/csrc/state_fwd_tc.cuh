@@ -27,6 +27,8 @@
 //                       5. wait D_FULL -> tcgen05.ld of the node's DP accumulators -> bias / activation / affine -> 256-bit
 //                          stores of the new state (+ NVLink peer stores) + convergence test against the own row still in
 //                          registers (+ BatchNormalization batch statistics when training).
+//   peer-copy warps (2): node-range partition only: forward the new rows of a tile to the peers that gather from them (512
+//                     contiguous bytes per instruction and peer over NVLink), decoupled from the compute warps.
 //   MMA warp     (1): one thread: wait A_FULL -> 27 x tcgen05.mma.kind::tf32 (A from tensor memory, B = weights in shared
 //                     memory, canonical K-major layout, pre-split hi / lo): D = A_hi B_hi + A_lo B_hi + A_hi B_lo ->
 //                     tcgen05.commit -> mbarrier D_FULL.
@@ -92,6 +94,11 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8])
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ float4 lds4(unsigned addr) {      // volatile: stays where it is written (loads ahead of the adds that consume them)
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
 }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
@@ -178,7 +185,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) state_iter_tc_kernel(const Iter
     __shared__ int s_flag;
     __shared__ uint32_t s_tmem;
     __shared__ __align__(8) uint64_t bar_landed[TC_SLOTS], bar_free[TC_SLOTS], bar_cols[TC_COLQ], bar_colfree[TC_COLQ], bar_rows[TC_ROWQ], bar_rowfree[TC_ROWQ],
-        bar_aggfull[TC_AGGQ], bar_aggfree[TC_AGGQ], bar_afull[TC_QUADS], bar_dfull[TC_QUADS];
+        bar_aggfull[TC_AGGQ], bar_aggfree[TC_AGGQ], bar_afull[TC_QUADS], bar_dfull[TC_QUADS], bar_stored[TC_QUADS], bar_copydone;
 
     // B operand: element (n, k) of k-step ks at [ks][k / 4 (piece)][n / 8][n % 8][k % 4]; K order = [x | agg | cst]
     for (int i = tid; i < KSTEPS * DP * 8; i += TC_THREADS) {
@@ -206,7 +213,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) state_iter_tc_kernel(const Iter
         for (int i = 0; i < TC_COLQ; ++i) { mbar_init(&bar_cols[i], 1); mbar_init(&bar_colfree[i], WS_NSUB); }
         for (int i = 0; i < TC_ROWQ; ++i) { mbar_init(&bar_rows[i], 1); mbar_init(&bar_rowfree[i], 2 * WS_NSUB); }   // 4 issue + 4 sum warps
         for (int i = 0; i < TC_AGGQ; ++i) { mbar_init(&bar_aggfull[i], 1); mbar_init(&bar_aggfree[i], 1); }
-        for (int i = 0; i < TC_QUADS; ++i) { mbar_init(&bar_afull[i], 4); mbar_init(&bar_dfull[i], 1); }
+        for (int i = 0; i < TC_QUADS; ++i) { mbar_init(&bar_afull[i], 4); mbar_init(&bar_dfull[i], 1); mbar_init(&bar_stored[i], 4); }
+        mbar_init(&bar_copydone, 2);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) tmem_alloc(&s_tmem, TC_TMEM_COLS);
@@ -224,7 +232,35 @@ __global__ void __launch_bounds__(TC_THREADS, 1) state_iter_tc_kernel(const Iter
     const int stage_cols = (DP + 2 * KA + 63) & ~63;      // TMEM columns of one quad: D | A_hi | A_lo (D aligned to its own width)
 
     if (warp >= 22) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TC_REGS_IDLE));     // idle warps: registers back to their sub-partition
+        // ======================================= PEER-COPY WARPS (node-range partition) =======================================
+        // Single GPU: idle (registers back to their sub-partition).  Partitioned: warp h forwards the new rows of staging tile
+        // 2 t + h of every 128-node tile to the peers that gather from them, once the compute quad has stored them locally:
+        // 16 bytes per lane, 4 consecutive rows = 512 contiguous bytes per instruction and peer -- whole NVLink packets, issued
+        // while the compute warps work on the following tiles (the thread-per-node epilogue itself would scatter 32-byte pieces)
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TC_REGS_IDLE));
+        if (p.n_peers > 1) {
+            const int h = warp - 22, rg = lane / LPN, lig = lane % LPN;
+            for (int t = 0; t < ntl2; ++t) {
+                mbar_wait<GNN_TC_SLEEP>(&bar_stored[t & 1], (t >> 1) & 1);
+                const int s = 2 * t + h;
+                if (s >= ntl) continue;
+                const long long n0 = (t0 + s) * TN;
+                for (int r = rg; r < TN; r += GPW) {
+                    const long long node = n0 + r;
+                    if (node >= p.N) break;
+                    const uint32_t need = p.peer_mask ? __ldg(p.peer_mask + node) : 0xffffffffu;
+                    const size_t off = (size_t)(p.row_offset + node) * DP + 4 * lig;
+                    float4 v;
+                    asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p.x_out + off) : "memory");
+#pragma unroll
+                    for (int r2 = 0; r2 < GNN_MAX_PEERS; ++r2)
+                        if (r2 < p.n_peers && r2 != p.rank && ((need >> r2) & 1u)) *reinterpret_cast<float4*>(p.peer_out[r2] + off) = v;
+                }
+            }
+            __threadfence_system();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_copydone);
+        }
     } else if (warp == 21) {
         // ============================================== MMA WARP ===============================================
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TC_REGS_SMALL));
@@ -358,47 +394,69 @@ __global__ void __launch_bounds__(TC_THREADS, 1) state_iter_tc_kernel(const Iter
             const float* lb = land0 + ((size_t)slot * slotcap - a0) * DP + 4 * lig;
             float* out = agg0 + (size_t)e * WS_SUB * DP;
             if (!(p.ws_debug & 2)) {
-                // the NPG nodes of my lane group side by side: NPG independent accumulation chains (each one sums its rows in stored
-                // order), one row of every node per step -- the shared-memory loads of a step are independent of each other
                 const int i0 = WS_SUB * c + grpw * NPG;          // first node (of the staging tile) of my lane group
-                int rb[NPG + 1];
-#pragma unroll
-                for (int u = 0; u <= NPG; ++u) rb[u] = srow[i0 + u] - ebase;
-                float4 acc[NPG];
-                int len = 0;
-#pragma unroll
-                for (int u = 0; u < NPG; ++u) { acc[u] = make_float4(0.f, 0.f, 0.f, 0.f); len = max(len, min(rb[u + 1], a0 + cnt) - rb[u]); }
-                // two steps at a time: 2 NPG independent 128-bit loads first (the shared-memory pipe is shared with the landing copies,
-                // a load takes ~100 cycles under load), then the adds
-                int rend[NPG];
-#pragma unroll
-                for (int u = 0; u < NPG; ++u) rend[u] = min(rb[u + 1], a0 + cnt);
-#pragma unroll 1
-                for (int k = 0; k < len; k += 2) {
-                    float4 v[2][NPG];
-#pragma unroll
-                    for (int kk = 0; kk < 2; ++kk)
-#pragma unroll
-                        for (int u = 0; u < NPG; ++u) {
-                            const int r = rb[u] + k + kk;
-                            v[kk][u] = r < rend[u] ? ld4(lb + (ptrdiff_t)r * DP) : make_float4(0.f, 0.f, 0.f, 0.f);
-                        }
-#pragma unroll
-                    for (int kk = 0; kk < 2; ++kk)
-#pragma unroll
-                        for (int u = 0; u < NPG; ++u) acc[u] = add4_x2(acc[u], v[kk][u]);
-                }
-#pragma unroll
-                for (int u = 0; u < NPG; ++u) {
+                const int rlim = a0 + cnt;                        // rows of the sub-tile that landed in the slot
+                // one node finished: arcs that did not get ring rows (rare, very dense sub-tiles) by direct loads, weight, store
+                auto finish = [&](int u, float4 acc, int rb1) {
                     const int il = grpw * NPG + u, i = i0 + u;
-                    for (int r = max(rb[u], a0 + cnt); r < rb[u + 1]; ++r) {   // arcs that did not get ring rows: direct loads (rare, very dense sub-tiles)
+                    for (int r = max(srow[i] - ebase, rlim); r < rb1; ++r) {
                         const int sidx = __ldg(p.col + ebase + r);
-                        acc[u] = add4(acc[u], ldg4(p.x_in + (size_t)sidx * DP + 4 * lig));
+                        acc = add4(acc, ldg4(p.x_in + (size_t)sidx * DP + 4 * lig));
                     }
                     const float sc = sscale0[q8 * TN + i];
-                    acc[u].x *= sc; acc[u].y *= sc; acc[u].z *= sc; acc[u].w *= sc;
-                    if (p.agg_save && n0 + i < p.N) st4_hint(p.agg_save + (size_t)(n0 + i) * DP + 4 * lig, acc[u], stream_pol);
-                    st4(out + il * DP + 4 * (lig ^ (il & SWZ)), acc[u]);
+                    acc.x *= sc; acc.y *= sc; acc.z *= sc; acc.w *= sc;
+                    if (p.agg_save && n0 + i < p.N) st4_hint(p.agg_save + (size_t)(n0 + i) * DP + 4 * lig, acc, stream_pol);
+                    st4(out + il * DP + 4 * (lig ^ (il & SWZ)), acc);
+                };
+                // regular sub-tile (every one of its 16 nodes has the same number of rows, all of them in the slot -- k-NN graphs, the
+                // benchmark graph): the NPG nodes of my lane group side by side, software-pipelined in registers (the loads of step
+                // e + 1 are issued before the adds of step e: a shared-memory load takes ~200 cycles next to the landing copies)
+                const int r_first = srow[i0] - ebase;
+                const int d0 = srow[i0 + 1] - ebase - r_first;
+                bool regular = srow[i0 + NPG] - ebase <= rlim;
+#pragma unroll
+                for (int u = 1; u < NPG; ++u) regular &= (srow[i0 + u + 1] - srow[i0 + u]) == d0;
+                const int d_lane0 = __shfl_sync(0xffffffffu, d0, 0);      // (outside the && below: every lane must execute the shuffle)
+                if (__all_sync(0xffffffffu, regular && d0 == d_lane0)) {
+                    const unsigned a_first = smem_u32(lb) + (unsigned)r_first * (DP * 4);      // node u starts u * d0 rows further
+                    const unsigned node_step = (unsigned)d0 * (DP * 4);
+                    float4 acc[NPG], va[NPG], vb[NPG];
+#pragma unroll
+                    for (int u = 0; u < NPG; ++u) { acc[u] = make_float4(0.f, 0.f, 0.f, 0.f); va[u] = acc[u]; }
+                    if (d0 > 0) {
+#pragma unroll
+                        for (int u = 0; u < NPG; ++u) va[u] = lds4(a_first + u * node_step);
+                    }
+#pragma unroll 1
+                    for (int e = 0; e < d0; e += 2) {
+                        if (e + 1 < d0) {
+#pragma unroll
+                            for (int u = 0; u < NPG; ++u) vb[u] = lds4(a_first + u * node_step + (e + 1) * (DP * 4));
+                        }
+#pragma unroll
+                        for (int u = 0; u < NPG; ++u) acc[u] = add4_x2(acc[u], va[u]);
+                        if (e + 2 < d0) {
+#pragma unroll
+                            for (int u = 0; u < NPG; ++u) va[u] = lds4(a_first + u * node_step + (e + 2) * (DP * 4));
+                        }
+                        if (e + 1 < d0) {
+#pragma unroll
+                            for (int u = 0; u < NPG; ++u) acc[u] = add4_x2(acc[u], vb[u]);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < NPG; ++u) finish(u, acc[u], 0);
+                } else {
+                    // ragged sub-tile: node after node, rows in stored order, 4 loads in flight
+#pragma unroll 1
+                    for (int u = 0; u < NPG; ++u) {
+                        const int r0 = srow[i0 + u] - ebase, r1 = srow[i0 + u + 1] - ebase;
+                        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                        const int rl = min(r1, rlim);
+#pragma unroll 4
+                        for (int r = r0; r < rl; ++r) acc = add4_x2(acc, ld4(lb + (ptrdiff_t)r * DP));
+                        finish(u, acc, r1);
+                    }
                 }
             }
             __syncwarp();
@@ -540,11 +598,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) state_iter_tc_kernel(const Iter
 #pragma unroll
                     for (int e = 0; e < 8; ++e) v[e] = y[8 * i + e];
                     stg8(orow + 8 * i, v);
-                    if (p.n_peers > 1) {
-                        store_to_peers(p, node - 0, 8 * i, make_float4(v[0], v[1], v[2], v[3]));
-                        store_to_peers(p, node - 0, 8 * i + 4, make_float4(v[4], v[5], v[6], v[7]));
-                    }
                 }
+            }
+            if (p.n_peers > 1) {       // rows visible device-wide, then the peer-copy warps take over
+                __threadfence();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_stored[quad]);
             }
             if (p.bn_train) {
                 // column sums over my warp's 32 nodes (thread = node): butterfly transpose-reduce, 31 + 31 shuffles; lane j ends
@@ -589,9 +648,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) state_iter_tc_kernel(const Iter
             }
         } else {
             if (p.go_next && __any_sync(0xffffffffu, any_moving) && lane == 0) s_flag = 1;
-            if (p.n_peers > 1) __threadfence_system();
             named_bar_sync(GNN_BAR_MLP_ALL, TC_COMPUTE);
-            if (tid == 0) iter_end(p, s_flag);
+            if (tid == 0) {
+                if (p.n_peers > 1) mbar_wait<GNN_TC_SLEEP>(&bar_copydone, 0);     // every row of this CTA has been stored into the peers
+                iter_end(p, s_flag);
+            }
         }
         tc_fence_before();
     }
