@@ -185,7 +185,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) state_iter_tc_kernel(const Iter
     __shared__ int s_flag;
     __shared__ uint32_t s_tmem;
     __shared__ __align__(8) uint64_t bar_landed[TC_SLOTS], bar_free[TC_SLOTS], bar_cols[TC_COLQ], bar_colfree[TC_COLQ], bar_rows[TC_ROWQ], bar_rowfree[TC_ROWQ],
-        bar_aggfull[TC_AGGQ], bar_aggfree[TC_AGGQ], bar_afull[TC_QUADS], bar_dfull[TC_QUADS], bar_stored[TC_QUADS], bar_copydone;
+        bar_aggfull[TC_AGGQ], bar_aggfree[TC_AGGQ], bar_afull[TC_QUADS], bar_xfull[TC_QUADS], bar_dfull[TC_QUADS], bar_copydone;
+    __shared__ int s_stored[TC_QUADS];                   // warps of quad g that have stored their rows of a tile, counted over all its tiles
 
     // B operand: element (n, k) of k-step ks at [ks][k / 4 (piece)][n / 8][n % 8][k % 4]; K order = [x | agg | cst]
     for (int i = tid; i < KSTEPS * DP * 8; i += TC_THREADS) {
@@ -213,7 +214,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) state_iter_tc_kernel(const Iter
         for (int i = 0; i < TC_COLQ; ++i) { mbar_init(&bar_cols[i], 1); mbar_init(&bar_colfree[i], WS_NSUB); }
         for (int i = 0; i < TC_ROWQ; ++i) { mbar_init(&bar_rows[i], 1); mbar_init(&bar_rowfree[i], 2 * WS_NSUB); }   // 4 issue + 4 sum warps
         for (int i = 0; i < TC_AGGQ; ++i) { mbar_init(&bar_aggfull[i], 1); mbar_init(&bar_aggfree[i], 1); }
-        for (int i = 0; i < TC_QUADS; ++i) { mbar_init(&bar_afull[i], 4); mbar_init(&bar_dfull[i], 1); mbar_init(&bar_stored[i], 4); }
+        for (int i = 0; i < TC_QUADS; ++i) { mbar_init(&bar_afull[i], 4); mbar_init(&bar_xfull[i], 4); mbar_init(&bar_dfull[i], 1); s_stored[i] = 0; }
         mbar_init(&bar_copydone, 2);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -241,7 +242,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) state_iter_tc_kernel(const Iter
         if (p.n_peers > 1) {
             const int h = warp - 22, rg = lane / LPN, lig = lane % LPN;
             for (int t = 0; t < ntl2; ++t) {
-                mbar_wait<GNN_TC_SLEEP>(&bar_stored[t & 1], (t >> 1) & 1);
+                // a COUNTER, not an mbarrier: nothing holds the compute quads back, so they may run several tiles ahead of the NVLink
+                // stores -- a parity wait cannot tell phase k from phase k + 2 and would wait for ever at the end
+                while (*reinterpret_cast<volatile int*>(&s_stored[t & 1]) < 4 * ((t >> 1) + 1)) __nanosleep(GNN_TC_SLEEP);
+                __threadfence();
                 const int s = 2 * t + h;
                 if (s >= ntl) continue;
                 const long long n0 = (t0 + s) * TN;
@@ -270,15 +274,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) state_iter_tc_kernel(const Iter
             for (int t = 0; t < ntl2; ++t) {
                 const int quad = t & 1;
                 const uint32_t d = tmem_base + quad * stage_cols, a_hi = d + DP, a_lo = a_hi + KA;
-                mbar_wait<GNN_TC_SLEEP>(&bar_afull[quad], (t >> 1) & 1);
-                tc_fence_after();
-                for (int ks = 0; ks < KSTEPS; ++ks) {
+                // the own-state / constant-row part of the contraction starts as soon as those columns are staged (before the
+                // aggregates exist); the aggregated-state part follows -- only 3 KX instructions sit behind the segment sums
+                auto mma3 = [&](int ks, bool first) {
                     const uint64_t bhi = tc_smem_desc(reinterpret_cast<const char*>(sBhi) + (size_t)ks * kstep_bytes, (DP / 8) * 128, 128);
                     const uint64_t blo = tc_smem_desc(reinterpret_cast<const char*>(sBlo) + (size_t)ks * kstep_bytes, (DP / 8) * 128, 128);
-                    tc_mma_tf32_ts(d, a_hi + 8 * ks, bhi, idesc, ks > 0);
+                    tc_mma_tf32_ts(d, a_hi + 8 * ks, bhi, idesc, first ? 0u : 1u);
                     tc_mma_tf32_ts(d, a_lo + 8 * ks, bhi, idesc, 1);
                     tc_mma_tf32_ts(d, a_hi + 8 * ks, blo, idesc, 1);
-                }
+                };
+                mbar_wait(&bar_xfull[quad], (t >> 1) & 1);
+                tc_fence_after();
+                for (int ks = 0; ks < KX; ++ks) mma3(ks, ks == 0);                  // own state: k-steps [0, KX)
+                for (int ks = 2 * KX; ks < KSTEPS; ++ks) mma3(ks, false);           // constant row: k-steps [2 KX, KSTEPS)
+                mbar_wait(&bar_afull[quad], (t >> 1) & 1);
+                tc_fence_after();
+                for (int ks = KX; ks < 2 * KX; ++ks) mma3(ks, false);               // aggregated state: k-steps [KX, 2 KX)
                 tc_commit(&bar_dfull[quad]);              // arrives once every MMA above has completed (accumulator ready, A free)
             }
         }
@@ -508,45 +519,48 @@ __global__ void __launch_bounds__(TC_THREADS, 1) state_iter_tc_kernel(const Iter
             const long long node = n0 + 16 * c0 + lane;       // MY node (thread = node from the operand staging on)
             const bool valid = have && node < p.N;
 
-            // 2. my 32 aggregate rows = FIFO entries of sub-tiles j0, j0 + 1 (written by sum warps c0, c0 + 1)
+            // 2. thread = node: hi / lo split of my own state row and constant row -> tensor memory (the quad's previous tile is
+            //    complete: its D_FULL was awaited by this very warp before its epilogue); the MMA warp starts on them at once
+            uint32_t hi[8], lo[8];
+            auto split8 = [&](const float* v) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) { hi[e] = __float_as_uint(v[e]) & 0xffffe000u; lo[e] = __float_as_uint(v[e] - __uint_as_float(hi[e])); }
+            };
+#pragma unroll
+            for (int i = 0; i < KX; ++i) {                 // own state: columns [0, DP)
+                split8(xn + 8 * i);
+                tmem_st8(a_hi + 8 * i, hi); tmem_st8(a_lo + 8 * i, lo);
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i)                    // constant row: columns [2 DP, 2 DP + 8 CS)
+                if (i < CS) {
+                    split8(cn + 8 * i);
+                    tmem_st8(a_hi + 2 * DP + 8 * i, hi); tmem_st8(a_lo + 2 * DP + 8 * i, lo);
+                }
+            tmem_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_xfull[quad]);
+            prefetch_own(t + TC_QUADS);        // next tile's rows: in flight during the rest of this tile
+
+            // 3. my 32 aggregate rows = FIFO entries of sub-tiles j0, j0 + 1 (written by sum warps c0, c0 + 1) -> tensor memory
             const int j0 = WS_NSUB * s + c0, e0 = j0 & (TC_AGGQ - 1);
             if (have) {
                 mbar_wait<GNN_TC_SLEEP>(&bar_aggfull[e0], (j0 / TC_AGGQ) & 1);
                 mbar_wait<GNN_TC_SLEEP>(&bar_aggfull[e0 + 1], (j0 / TC_AGGQ) & 1);
             }
-
-            // 3. + 4. thread = node: aggregate row out of the scratch, hi / lo split of [x | agg | cst] -> tensor memory
-            //    (the quad's previous tile is complete: its D_FULL was awaited by this very warp before its epilogue)
-            {
-                uint32_t hi[8], lo[8];
-                auto split8 = [&](const float* v) {
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) { hi[e] = __float_as_uint(v[e]) & 0xffffe000u; lo[e] = __float_as_uint(v[e] - __uint_as_float(hi[e])); }
-                };
+            for (int i = 0; i < KX; ++i) {                 // aggregated state: columns [DP, 2 DP)
+                float v[8];
+                const float* arow = agg0 + ((size_t)e0 * WS_SUB + lane) * DP;      // entries e0, e0 + 1 are adjacent: row `lane` of the pair
+                const float4 g0 = ld4(arow + 4 * ((2 * i) ^ (lane & SWZ))), g1 = ld4(arow + 4 * ((2 * i + 1) ^ (lane & SWZ)));
+                v[0] = g0.x; v[1] = g0.y; v[2] = g0.z; v[3] = g0.w; v[4] = g1.x; v[5] = g1.y; v[6] = g1.z; v[7] = g1.w;
+                if (!have) {
 #pragma unroll
-                for (int i = 0; i < KX; ++i) {                 // own state: columns [0, DP)
-                    split8(xn + 8 * i);
-                    tmem_st8(a_hi + 8 * i, hi); tmem_st8(a_lo + 8 * i, lo);
+                    for (int e = 0; e < 8; ++e) v[e] = 0.f;
                 }
-#pragma unroll
-                for (int i = 0; i < KX; ++i) {                 // aggregated state: columns [DP, 2 DP)
-                    float v[8];
-                    const float* arow = agg0 + ((size_t)e0 * WS_SUB + lane) * DP;      // entries e0, e0 + 1 are adjacent: row `lane` of the pair
-                    const float4 g0 = ld4(arow + 4 * ((2 * i) ^ (lane & SWZ))), g1 = ld4(arow + 4 * ((2 * i + 1) ^ (lane & SWZ)));
-                    v[0] = g0.x; v[1] = g0.y; v[2] = g0.z; v[3] = g0.w; v[4] = g1.x; v[5] = g1.y; v[6] = g1.z; v[7] = g1.w;
-                    if (!have) {
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) v[e] = 0.f;
-                    }
-                    split8(v);
-                    tmem_st8(a_hi + DP + 8 * i, hi); tmem_st8(a_lo + DP + 8 * i, lo);
-                }
-#pragma unroll
-                for (int i = 0; i < 2; ++i)                    // constant row: columns [2 DP, 2 DP + 8 CS)
-                    if (i < CS) {
-                        split8(cn + 8 * i);
-                        tmem_st8(a_hi + 2 * DP + 8 * i, hi); tmem_st8(a_lo + 2 * DP + 8 * i, lo);
-                    }
+                split8(v);
+                tmem_st8(a_hi + DP + 8 * i, hi); tmem_st8(a_lo + DP + 8 * i, lo);
             }
             tmem_wait_st();
             tc_fence_before();
@@ -555,7 +569,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) state_iter_tc_kernel(const Iter
                 if (have) { mbar_arrive(&bar_aggfree[e0]); mbar_arrive(&bar_aggfree[e0 + 1]); }     // FIFO entries back to the sum warps
                 mbar_arrive(&bar_afull[quad]);
             }
-            prefetch_own(t + TC_QUADS);        // next tile's rows: in flight while the tensor core works and during the epilogue
 
             // 5. epilogue: my node's DP accumulators -> bias / activation / affine -> store + convergence test
             mbar_wait<GNN_TC_SLEEP>(&bar_dfull[quad], (t >> 1) & 1);
@@ -603,7 +616,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) state_iter_tc_kernel(const Iter
             if (p.n_peers > 1) {       // rows visible device-wide, then the peer-copy warps take over
                 __threadfence();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&bar_stored[quad]);
+                if (lane == 0) atomicAdd(&s_stored[quad], 1);
             }
             if (p.bn_train) {
                 // column sums over my warp's 32 nodes (thread = node): butterfly transpose-reduce, 31 + 31 shuffles; lane j ends
