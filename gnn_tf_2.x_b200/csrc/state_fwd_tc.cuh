@@ -249,16 +249,39 @@ __global__ void __launch_bounds__(TC_THREADS, 1) state_iter_tc_kernel(const Iter
                 const int s = 2 * t + h;
                 if (s >= ntl) continue;
                 const long long n0 = (t0 + s) * TN;
-                for (int r = rg; r < TN; r += GPW) {
-                    const long long node = n0 + r;
-                    if (node >= p.N) break;
-                    const uint32_t need = p.peer_mask ? __ldg(p.peer_mask + node) : 0xffffffffu;
-                    const size_t off = (size_t)(p.row_offset + node) * DP + 4 * lig;
-                    float4 v;
-                    asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p.x_out + off) : "memory");
+                // which peers gather from which of the 64 rows: one load per lane and half tile (not one dependent load per row);
+                // a tile none of whose rows travels (the interior of a locality-friendly partition) costs two loads and a vote
+                uint32_t need[2];
 #pragma unroll
-                    for (int r2 = 0; r2 < GNN_MAX_PEERS; ++r2)
-                        if (r2 < p.n_peers && r2 != p.rank && ((need >> r2) & 1u)) *reinterpret_cast<float4*>(p.peer_out[r2] + off) = v;
+                for (int hh = 0; hh < 2; ++hh) {
+                    const long long node = n0 + 32 * hh + lane;
+                    need[hh] = node < p.N ? (p.peer_mask ? __ldg(p.peer_mask + node) : 0xffffffffu) : 0u;
+                    need[hh] &= ~(1u << p.rank) & ((1u << p.n_peers) - 1u);
+                }
+                if (!__any_sync(0xffffffffu, (need[0] | need[1]) != 0u)) continue;
+                // 4 row groups at a time: 4 independent 16-byte loads per lane in flight, then the stores (GPW rows per group)
+                for (int r0 = 0; r0 < TN; r0 += 4 * GPW) {
+                    float4 v[4];
+                    uint32_t nd[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int r = r0 + k * GPW + rg;
+                        const uint32_t nlo = __shfl_sync(0xffffffffu, need[0], r & 31), nhi = __shfl_sync(0xffffffffu, need[1], r & 31);
+                        nd[k] = (r >> 5) ? nhi : nlo;
+                        v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (nd[k]) {
+                            const size_t off = (size_t)(p.row_offset + n0 + r) * DP + 4 * lig;
+                            asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[k].x), "=f"(v[k].y), "=f"(v[k].z), "=f"(v[k].w) : "l"(p.x_out + off) : "memory");
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        if (!nd[k]) continue;
+                        const size_t off = (size_t)(p.row_offset + n0 + r0 + k * GPW + rg) * DP + 4 * lig;
+#pragma unroll
+                        for (int r2 = 0; r2 < GNN_MAX_PEERS; ++r2)
+                            if ((nd[k] >> r2) & 1u) *reinterpret_cast<float4*>(p.peer_out[r2] + off) = v[k];
+                    }
                 }
             }
             __threadfence_system();

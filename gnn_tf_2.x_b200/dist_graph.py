@@ -60,8 +60,23 @@ class HaloPlan:
         self.rank, self.world, self.group, self.bounds = rank, world, group, bounds
         lo, hi = bounds[rank], bounds[rank + 1]
         device = cols.device
-        cols = cols.to(torch.int64)
-        needed = torch.unique(cols[(cols < lo) | (cols >= hi)])                     # sorted remote rows this rank gathers from
+        self.lo, self.hi = lo, hi
+        # remote rows this rank gathers from: a bitmap over the nodes (one scatter over the arcs, no sort)
+        wanted = torch.zeros(bounds[-1], dtype=torch.bool, device=device)
+        if cols.numel(): wanted[cols.to(torch.int64)] = True
+        wanted[lo:hi] = False
+        # all-gather instead of all-to-all when most remote rows are needed anyway (uniform-random graphs): decided first, because
+        # then nobody needs the row lists and their two all-to-all exchanges
+        sizes = [bounds[r + 1] - bounds[r] for r in range(world)]
+        remote = bounds[-1] - (hi - lo)
+        frac = (wanted.sum().to(torch.float32) / max(remote, 1)).reshape(1)
+        dist.all_reduce(frac, op=dist.ReduceOp.MAX, group=group)
+        self.use_allgather = bool(frac.item() > allgather_threshold) and len(set(sizes)) == 1
+        if self.use_allgather:
+            self.recv_rows = self.send_rows = None
+            self.recv_counts = self.send_counts = None
+            return
+        needed = torch.nonzero(wanted, as_tuple=False)[:, 0]                         # sorted
         edges = torch.as_tensor(bounds[1:], dtype=torch.int64, device=device)
         owner = torch.bucketize(needed, edges, right=True)
         recv_counts = torch.bincount(owner, minlength=world)[:world]
@@ -71,13 +86,6 @@ class HaloPlan:
         send_rows = torch.empty(int(sum(self.send_counts)), dtype=torch.int64, device=device)
         dist.all_to_all_single(send_rows, needed, output_split_sizes=self.send_counts, input_split_sizes=self.recv_counts, group=group)
         self.recv_rows, self.send_rows = needed, send_rows                          # global ids, grouped by peer rank
-        # all-gather instead of all-to-all when most remote rows are needed anyway (uniform-random graphs)
-        sizes = [bounds[r + 1] - bounds[r] for r in range(world)]
-        remote = bounds[-1] - (hi - lo)
-        frac = torch.tensor([needed.numel() / max(remote, 1)], device=device)
-        dist.all_reduce(frac, op=dist.ReduceOp.MAX, group=group)
-        self.use_allgather = bool(frac.item() > allgather_threshold) and len(set(sizes)) == 1
-        self.lo, self.hi = lo, hi
 
     def exchange(self, x_full: torch.Tensor) -> None:
         """ make the rows of x_full that this rank gathers from valid (its own rows [lo, hi) were just computed) """
