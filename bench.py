@@ -675,6 +675,7 @@ def main():
                          _endpoints=(wl2['src'], wl2['dst']))
         gt2 = GraphTensor.fromGraphObject(g2, device=device)
         gnn.initial_state = torch.as_tensor(wl2['x0'], device=device)
+        gnn.net_state.set_weights(wl2['ws']); gnn.net_output.set_weights(wl2['wo'])     # this workload's own nets (the train leg moved the others)
         if parity is not None:
             parity[other] = parity_check(wl2, gnn, gt2, device, args.parity_iterations, training=False)
             parity[other]['kernel'] = _native.last_forward_kernel()

@@ -25,10 +25,9 @@
 //                       4. hi / lo split (hi = tf32 part, lo = exact remainder) of [x | agg | cst] -> tcgen05.st into the quad's
 //                          A operand in tensor memory (144 columns), mbarrier A_FULL,
 //                       5. wait D_FULL -> tcgen05.ld of the node's DP accumulators -> bias / activation / affine -> 256-bit
-//                          stores of the new state (+ NVLink peer stores) + convergence test against the own row still in
+//                          stores of the new state (node-range partition: the same stores into every peer whose bit is set
+//                          in the node's peer mask, over NVLink) + convergence test against the own row still in
 //                          registers (+ BatchNormalization batch statistics when training).
-//   peer-copy warps (2): node-range partition only: forward the new rows of a tile to the peers that gather from them (512
-//                     contiguous bytes per instruction and peer over NVLink), decoupled from the compute warps.
 //   MMA warp     (1): one thread: wait A_FULL -> 27 x tcgen05.mma.kind::tf32 (A from tensor memory, B = weights in shared
 //                     memory, canonical K-major layout, pre-split hi / lo): D = A_hi B_hi + A_lo B_hi + A_hi B_lo ->
 //                     tcgen05.commit -> mbarrier D_FULL.
@@ -185,8 +184,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) state_iter_tc_kernel(const Iter
     __shared__ int s_flag;
     __shared__ uint32_t s_tmem;
     __shared__ __align__(8) uint64_t bar_landed[TC_SLOTS], bar_free[TC_SLOTS], bar_cols[TC_COLQ], bar_colfree[TC_COLQ], bar_rows[TC_ROWQ], bar_rowfree[TC_ROWQ],
-        bar_aggfull[TC_AGGQ], bar_aggfree[TC_AGGQ], bar_afull[TC_QUADS], bar_xfull[TC_QUADS], bar_dfull[TC_QUADS], bar_copydone;
-    __shared__ int s_stored[TC_QUADS];                   // warps of quad g that have stored their rows of a tile, counted over all its tiles
+        bar_aggfull[TC_AGGQ], bar_aggfree[TC_AGGQ], bar_afull[TC_QUADS], bar_xfull[TC_QUADS], bar_dfull[TC_QUADS];
 
     // B operand: element (n, k) of k-step ks at [ks][k / 4 (piece)][n / 8][n % 8][k % 4]; K order = [x | agg | cst]
     for (int i = tid; i < KSTEPS * DP * 8; i += TC_THREADS) {
@@ -214,8 +212,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) state_iter_tc_kernel(const Iter
         for (int i = 0; i < TC_COLQ; ++i) { mbar_init(&bar_cols[i], 1); mbar_init(&bar_colfree[i], WS_NSUB); }
         for (int i = 0; i < TC_ROWQ; ++i) { mbar_init(&bar_rows[i], 1); mbar_init(&bar_rowfree[i], 2 * WS_NSUB); }   // 4 issue + 4 sum warps
         for (int i = 0; i < TC_AGGQ; ++i) { mbar_init(&bar_aggfull[i], 1); mbar_init(&bar_aggfree[i], 1); }
-        for (int i = 0; i < TC_QUADS; ++i) { mbar_init(&bar_afull[i], 4); mbar_init(&bar_xfull[i], 4); mbar_init(&bar_dfull[i], 1); s_stored[i] = 0; }
-        mbar_init(&bar_copydone, 2);
+        for (int i = 0; i < TC_QUADS; ++i) { mbar_init(&bar_afull[i], 4); mbar_init(&bar_xfull[i], 4); mbar_init(&bar_dfull[i], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) tmem_alloc(&s_tmem, TC_TMEM_COLS);
@@ -233,61 +230,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) state_iter_tc_kernel(const Iter
     const int stage_cols = (DP + 2 * KA + 63) & ~63;      // TMEM columns of one quad: D | A_hi | A_lo (D aligned to its own width)
 
     if (warp >= 22) {
-        // ======================================= PEER-COPY WARPS (node-range partition) =======================================
-        // Single GPU: idle (registers back to their sub-partition).  Partitioned: warp h forwards the new rows of staging tile
-        // 2 t + h of every 128-node tile to the peers that gather from them, once the compute quad has stored them locally:
-        // 16 bytes per lane, 4 consecutive rows = 512 contiguous bytes per instruction and peer -- whole NVLink packets, issued
-        // while the compute warps work on the following tiles (the thread-per-node epilogue itself would scatter 32-byte pieces)
+        // ============================================== IDLE WARPS ==============================================
+        // Present only so that every SM sub-partition holds the same number of warps (setmaxnreg pools are per sub-partition);
+        // their registers go back to the pool.  Rows that other GPUs gather from are stored into the peers by the compute
+        // threads themselves (see the epilogue): a separate copy role was latency-bound -- the two CTAs at the edges of a
+        // locality-friendly partition forward 2048 rows each and finished 70 us after everybody else.
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TC_REGS_IDLE));
-        if (p.n_peers > 1) {
-            const int h = warp - 22, rg = lane / LPN, lig = lane % LPN;
-            for (int t = 0; t < ntl2; ++t) {
-                // a COUNTER, not an mbarrier: nothing holds the compute quads back, so they may run several tiles ahead of the NVLink
-                // stores -- a parity wait cannot tell phase k from phase k + 2 and would wait for ever at the end
-                while (*reinterpret_cast<volatile int*>(&s_stored[t & 1]) < 4 * ((t >> 1) + 1)) __nanosleep(GNN_TC_SLEEP);
-                __threadfence();
-                const int s = 2 * t + h;
-                if (s >= ntl) continue;
-                const long long n0 = (t0 + s) * TN;
-                // which peers gather from which of the 64 rows: one load per lane and half tile (not one dependent load per row);
-                // a tile none of whose rows travels (the interior of a locality-friendly partition) costs two loads and a vote
-                uint32_t need[2];
-#pragma unroll
-                for (int hh = 0; hh < 2; ++hh) {
-                    const long long node = n0 + 32 * hh + lane;
-                    need[hh] = node < p.N ? (p.peer_mask ? __ldg(p.peer_mask + node) : 0xffffffffu) : 0u;
-                    need[hh] &= ~(1u << p.rank) & ((1u << p.n_peers) - 1u);
-                }
-                if (!__any_sync(0xffffffffu, (need[0] | need[1]) != 0u)) continue;
-                // 4 row groups at a time: 4 independent 16-byte loads per lane in flight, then the stores (GPW rows per group)
-                for (int r0 = 0; r0 < TN; r0 += 4 * GPW) {
-                    float4 v[4];
-                    uint32_t nd[4];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const int r = r0 + k * GPW + rg;
-                        const uint32_t nlo = __shfl_sync(0xffffffffu, need[0], r & 31), nhi = __shfl_sync(0xffffffffu, need[1], r & 31);
-                        nd[k] = (r >> 5) ? nhi : nlo;
-                        v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (nd[k]) {
-                            const size_t off = (size_t)(p.row_offset + n0 + r) * DP + 4 * lig;
-                            asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[k].x), "=f"(v[k].y), "=f"(v[k].z), "=f"(v[k].w) : "l"(p.x_out + off) : "memory");
-                        }
-                    }
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        if (!nd[k]) continue;
-                        const size_t off = (size_t)(p.row_offset + n0 + r0 + k * GPW + rg) * DP + 4 * lig;
-#pragma unroll
-                        for (int r2 = 0; r2 < GNN_MAX_PEERS; ++r2)
-                            if ((nd[k] >> r2) & 1u) *reinterpret_cast<float4*>(p.peer_out[r2] + off) = v[k];
-                    }
-                }
-            }
-            __threadfence_system();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bar_copydone);
-        }
     } else if (warp == 21) {
         // ============================================== MMA WARP ===============================================
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TC_REGS_SMALL));
@@ -565,6 +513,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) state_iter_tc_kernel(const Iter
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_xfull[quad]);
             prefetch_own(t + TC_QUADS);        // next tile's rows: in flight during the rest of this tile
+            uint32_t need = 0u;                // peers that gather from MY node (direct peer stores)
+            if (p.n_peers > 1 && valid)
+                need = (p.peer_mask ? __ldg(p.peer_mask + node) : 0xffffffffu) & ~(1u << p.rank) & ((1u << p.n_peers) - 1u);
 
             // 3. my 32 aggregate rows = FIFO entries of sub-tiles j0, j0 + 1 (written by sum warps c0, c0 + 1) -> tensor memory
             const int j0 = WS_NSUB * s + c0, e0 = j0 & (TC_AGGQ - 1);
@@ -635,11 +586,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) state_iter_tc_kernel(const Iter
                     for (int e = 0; e < 8; ++e) v[e] = y[8 * i + e];
                     stg8(orow + 8 * i, v);
                 }
-            }
-            if (p.n_peers > 1) {       // rows visible device-wide, then the peer-copy warps take over
-                __threadfence();
-                __syncwarp();
-                if (lane == 0) atomicAdd(&s_stored[quad], 1);
+                while (need) {         // my row into every peer that gathers from it: plain remote stores, nothing waits on them
+                    const int r = __ffs(need) - 1;
+                    need &= need - 1u;
+                    float* prow = p.peer_out[r] + (size_t)(p.row_offset + node) * DP;
+#pragma unroll
+                    for (int i = 0; i < DP / 8; ++i) {
+                        float v[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) v[e] = y[8 * i + e];
+                        stg8(prow + 8 * i, v);
+                    }
+                }
             }
             if (p.bn_train) {
                 // column sums over my warp's 32 nodes (thread = node): butterfly transpose-reduce, 31 + 31 shuffles; lane j ends
@@ -684,11 +642,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) state_iter_tc_kernel(const Iter
             }
         } else {
             if (p.go_next && __any_sync(0xffffffffu, any_moving) && lane == 0) s_flag = 1;
+            if (p.n_peers > 1) __threadfence_system();      // my peer stores before the arrival mark of iter_end
             named_bar_sync(GNN_BAR_MLP_ALL, TC_COMPUTE);
-            if (tid == 0) {
-                if (p.n_peers > 1) mbar_wait<GNN_TC_SLEEP>(&bar_copydone, 0);     // every row of this CTA has been stored into the peers
-                iter_end(p, s_flag);
-            }
+            if (tid == 0) iter_end(p, s_flag);
         }
         tc_fence_before();
     }

@@ -582,7 +582,10 @@ class GraphTensor:
         """ shallow copy sharing the (immutable) device tensors, as the reference does (graph_class.py:347-351) """
         new = GraphTensor.__new__(GraphTensor)
         new.__dict__.update(self.__dict__)
-        new.__dict__['_index_cache'] = dict()
+        # the index cache is shared with the copy: its entries are keyed on the masks' storage and version, so a copy whose masks
+        # are replaced or edited rebuilds its own entries -- and the per-layer copies LGNN.Loop makes at every call find the
+        # indices already built (no torch.nonzero, i.e. no host sync, inside a captured training step)
+        new.__dict__['_index_cache'] = self.__dict__.setdefault('_index_cache', dict())
         return new
 
     # -----------------------------------------------------------------------------------------------------------------

@@ -162,7 +162,7 @@ def test_train_reduces_loss_and_keeps_history_keys():
     assert gnn.history['Epoch'][-1] == 30
 
 
-@pytest.mark.parametrize('problem', ['n', 'g'])
+@pytest.mark.parametrize('problem', ['n', 'g', 'lgnn'])
 def test_cuda_graph_training_step_equals_eager(problem):
     """ use_cuda_graph: the whole training step captured once per batch graph and replayed (while_loop launches, BPTT sweep,
     output net, Adam).  Dropout masks and the Adam step counter must advance at every replay exactly as in eager mode:
@@ -173,17 +173,26 @@ def test_cuda_graph_training_step_equals_eager(problem):
     from gnn_b200.GNN import GNNnodeBased, GNNgraphBased
     from gnn_b200.graph_class import GraphTensor
     from gnn_b200.keras_compat import Adam, categorical_crossentropy
+    lgnn, problem = problem == 'lgnn', 'n' if problem == 'lgnn' else problem
     graphs = _toy_dataset(problem, n_graphs=18, seed=9)
     batches = [GraphTensor.fromGraphObject(b) for b in utils.getbatches(graphs, problem, 'average', batch_size=6)]
 
-    def make():
-        f_s, l_s = get_inout_dims('state', 3, 1, 2, problem, 0, None)
-        f_o, l_o = get_inout_dims('output', 3, 1, 2, problem, 0, None)
-        net_s = MLP(f_s, l_s, 'selu', 'lecun_normal', 'lecun_normal', dropout_rate=0.1, dropout_pos=0, batch_normalization=True, seed=3)
-        net_o = MLP(f_o, l_o, 'softmax', 'glorot_normal', 'glorot_normal', dropout_rate=0.1, dropout_pos=0, batch_normalization=False, seed=4)
+    def one(layer, seed, **kw):
+        f_s, l_s = get_inout_dims('state', 3, 1, 2, problem, 0, None, **kw)
+        f_o, l_o = get_inout_dims('output', 3, 1, 2, problem, 0, None, **kw)
+        net_s = MLP(f_s, l_s, 'selu', 'lecun_normal', 'lecun_normal', dropout_rate=0.1, dropout_pos=0, batch_normalization=True, seed=seed)
+        net_o = MLP(f_o, l_o, 'softmax', 'glorot_normal', 'glorot_normal', dropout_rate=0.1, dropout_pos=0, batch_normalization=False, seed=seed + 1)
         cls = {'n': GNNnodeBased, 'g': GNNgraphBased}[problem]
         return cls(net_s, net_o, Adam(learning_rate=0.01), categorical_crossentropy, {'from_logits': False}, state_vect_dim=0, max_iteration=5,
-                   threshold=0.01, addressed_problem='c', path_writer='/tmp/gnn_b200_graphed/')
+                   threshold=0.01, addressed_problem='c', path_writer=f'/tmp/gnn_b200_graphed/{layer}/')
+
+    def make():
+        if not lgnn: return one(0, 3)
+        # 3-layer LGNN (get_output): every layer's loop, the graph updates between the layers and one Adam over all layers in ONE graph;
+        # the per-layer GraphTensor copies must find their index tensors cached (torch.nonzero cannot run inside a capture)
+        from gnn_b200.LGNN import LGNN
+        layers = [one(l, 3 + 2 * l, layer=l, get_state=False, get_output=True) for l in range(3)]
+        return LGNN(layers, False, True, Adam(learning_rate=0.01), categorical_crossentropy, {'from_logits': False}, 'c', path_writer='/tmp/gnn_b200_graphed/lgnn/')
 
     eager, graphed = make(), make()
     graphed.use_cuda_graph = True
@@ -196,7 +205,8 @@ def test_cuda_graph_training_step_equals_eager(problem):
     assert any(entry[0] == 'graph' for b in batches for entry in b.__dict__['_step_graphs'].values())
     for (k1, l1), (k2, l2) in zip(losses[id(eager)], losses[id(graphed)]):
         assert k1 == k2 and abs(l1 - l2) <= 1e-5 * max(1.0, abs(l1)), (k1, l1, k2, l2)
-    for w1, w2 in zip(eager.net_state.get_weights() + eager.net_output.get_weights(), graphed.net_state.get_weights() + graphed.net_output.get_weights()):
+    weights = lambda m: [w for x in (m.gnns if lgnn else [m]) for w in x.net_state.get_weights() + x.net_output.get_weights()]
+    for w1, w2 in zip(weights(eager), weights(graphed)):
         np.testing.assert_allclose(w2, w1, rtol=2e-5, atol=2e-6)
 
 
