@@ -15,7 +15,8 @@ import numpy as np
 import torch
 
 GNN_MAX_LAYERS = 4
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'libgnn_b200.so')
+# GNN_B200_LIBRARY: another build of the same ABI (comparison runs of an older kernel on the same box)
+_LIB_PATH = os.environ.get('GNN_B200_LIBRARY') or os.path.join(os.path.dirname(os.path.abspath(__file__)), 'libgnn_b200.so')
 _lib: Optional[C.CDLL] = None
 
 ACT_CODES = {'linear': 0, 'relu': 1, 'tanh': 2, 'sigmoid': 3, 'selu': 4, 'elu': 5, 'softmax': 6, 'softplus': 7}
@@ -64,7 +65,8 @@ EXCHANGE_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int32, C.c_int64, C.c_int64)
 # every symbol include/gnn_b200.h declares (tests check that the library exports all of them)
 EXPORTED_SYMBOLS = ['gnn_last_error', 'gnn_abi_version', 'gnn_device_info', 'gnn_csr_build', 'gnn_spmm',
                     'gnn_state_loop_workspace_bytes', 'gnn_state_loop_layout', 'gnn_state_loop_forward', 'gnn_state_loop_backward',
-                    'gnn_launch_count', 'gnn_profile_iterations', 'gnn_profile_last_iterations', 'gnn_last_forward_kernel']
+                    'gnn_launch_count', 'gnn_profile_iterations', 'gnn_profile_last_iterations', 'gnn_last_forward_kernel',
+                    'gnn_last_backward_kernel']
 
 
 def library_path() -> str: return _LIB_PATH
@@ -80,6 +82,7 @@ def lib() -> C.CDLL:
         l = C.CDLL(_LIB_PATH)
         l.gnn_last_error.restype = C.c_char_p
         l.gnn_last_forward_kernel.restype = C.c_char_p
+        l.gnn_last_backward_kernel.restype = C.c_char_p
         l.gnn_abi_version.restype = C.c_int
         l.gnn_launch_count.restype = C.c_int64
         l.gnn_launch_count.argtypes = [C.c_int32]
@@ -140,6 +143,10 @@ def set_seed(args: 'gnn_loop_args', seed) -> None:
 
 def last_forward_kernel() -> str:
     return lib().gnn_last_forward_kernel().decode()
+
+
+def last_backward_kernel() -> str:
+    return lib().gnn_last_backward_kernel().decode()
 
 
 def profile_iterations(enable: bool) -> None:

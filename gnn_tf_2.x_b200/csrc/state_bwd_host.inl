@@ -68,6 +68,21 @@ extern "C" int gnn_state_loop_backward(const gnn_graph* g, const gnn_mlp* net, c
         ts = TileShape{32, 32};
     }
     if (!node_kernel) GNN_FAIL(GNN_ERR_UNSUPPORTED, "no backward kernel for padded state width %d", lay.DP);
+    // single Dense layer without active dropout on a graph that fills the GPU: the pipelined kernel of state_bwd_l1.cuh
+    // (GNN_B200_BWD=phased keeps the phase-structured kernel: comparison runs)
+    {
+        const char* env = getenv("GNN_B200_BWD");
+        if (ks->bwd_node_l1 && bwd_l1_applicable(lay, a->training != 0, y_saved) && N >= 64LL * di.sms && !(env && !strcmp(env, "phased")) &&
+            bwd_l1_smem_bytes(lay) <= (size_t)di.smem_optin) {
+            node_kernel = ks->bwd_node_l1;
+            ts = TileShape{BL_TN, BL_NT};
+            smem = bwd_l1_smem_bytes(lay);
+            p.SU = bwd_l1_su(lay);
+            p.SD = bwd_l1_sd(lay);
+        }
+    }
+    snprintf(g_last_bwd_kernel, sizeof(g_last_bwd_kernel), node_kernel == ks->bwd_node_l1 ? "state_bwd_node_l1_kernel<%d>" : "state_bwd_node_kernel<%d,%d,%d>",
+             lay.DP, ts.tn, ts.nt);
     int occ = 0;
     GNN_TRY(kernel_occupancy((const void*)node_kernel, ts.nt, smem, &occ));
     const long long ntiles = (N + ts.tn - 1) / ts.tn;

@@ -151,10 +151,13 @@ static inline size_t tc_weight_floats(const NetLayout& lay) { return (size_t)tc_
 static inline size_t tc_smem_bytes(const NetLayout& lay, int ring, int capc, bool bn_train) {
     size_t fl = tc_weight_floats(lay) + (size_t)TC_AGGQ * WS_SUB * lay.DP + (size_t)ring * lay.DP + TC_ROWQ * 68 + TC_ROWQ * WS_TN +
                 TC_COLQ * (size_t)(capc + WS_COLPAD) + (bn_train ? (size_t)(TC_COMPUTE / 32) * 2 * lay.DP * 2 : 0);
-    return fl * 4;   // weights, aggregate FIFO (16 sub-tiles), ring, row pointers / scales, arc sources, BN sums (fp64)
+    return fl * 4 + 128;   // weights, aggregate FIFO (16 sub-tiles), ring, row pointers / scales, arc sources, BN sums (fp64); + alignment slack
 }
 
-template <int DP>
+// PEERS: node-range partition over several GPUs (rows other ranks gather from are also stored into their memory).  A template
+// parameter, not a run-time test: the remote stores in the epilogue of the compute warps (capped at 128 registers) cost the
+// single-GPU kernel 12 % when they were merely branched around.
+template <int DP, bool PEERS>
 __global__ void __launch_bounds__(TC_THREADS, 1) state_iter_tc_kernel(const IterParams p) {
     constexpr int TN = WS_TN, LPN = DP / 4;      // 64-node staging tiles, 16-node sub-tiles (as state_fwd_ws.cuh)
     constexpr int GPW = 32 / LPN;                // source rows per warp-wide cp.async / lane groups per warp
@@ -170,7 +173,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) state_iter_tc_kernel(const Iter
     const int CS = (CP + 7) / 8, KSTEPS = 2 * KX + CS, KA = 8 * KSTEPS;      // A columns per copy (hi or lo)
     const int nslot = p.ring_slots, slotcap = p.slot_rows;
 
-    extern __shared__ __align__(128) float smem[];
+    // The dynamic shared memory starts right behind the static variables: only 16-byte alignment is guaranteed (an alignment
+    // attribute on the extern array does not move it).  With the base at 112 mod 128 every 128-byte state row of the landing ring
+    // straddled two shared-memory lines and the whole kernel ran 15 % slower: align by hand (tc_smem_bytes reserves the slack).
+    extern __shared__ __align__(16) float smem_raw[];
+    float* smem = smem_raw + (((128u - ((unsigned)__cvta_generic_to_shared(smem_raw) & 127u)) & 127u) >> 2);
     float* sBhi = smem;                                  // [KSTEPS][2][DP / 8][8][4]
     float* sBlo = sBhi + (size_t)KSTEPS * DP * 8;
     float* sBias = sBlo + (size_t)KSTEPS * DP * 8;       // [DP]
@@ -514,7 +521,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) state_iter_tc_kernel(const Iter
             if (lane == 0) mbar_arrive(&bar_xfull[quad]);
             prefetch_own(t + TC_QUADS);        // next tile's rows: in flight during the rest of this tile
             uint32_t need = 0u;                // peers that gather from MY node (direct peer stores)
-            if (p.n_peers > 1 && valid)
+            if (PEERS && p.n_peers > 1 && valid)
                 need = (p.peer_mask ? __ldg(p.peer_mask + node) : 0xffffffffu) & ~(1u << p.rank) & ((1u << p.n_peers) - 1u);
 
             // 3. my 32 aggregate rows = FIFO entries of sub-tiles j0, j0 + 1 (written by sum warps c0, c0 + 1) -> tensor memory
@@ -586,7 +593,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) state_iter_tc_kernel(const Iter
                     for (int e = 0; e < 8; ++e) v[e] = y[8 * i + e];
                     stg8(orow + 8 * i, v);
                 }
-                while (need) {         // my row into every peer that gathers from it: plain remote stores, nothing waits on them
+                while (PEERS && need) {         // my row into every peer that gathers from it: plain remote stores, nothing waits on them
                     const int r = __ffs(need) - 1;
                     need &= need - 1u;
                     float* prow = p.peer_out[r] + (size_t)(p.row_offset + node) * DP;
@@ -642,7 +649,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) state_iter_tc_kernel(const Iter
             }
         } else {
             if (p.go_next && __any_sync(0xffffffffu, any_moving) && lane == 0) s_flag = 1;
-            if (p.n_peers > 1) __threadfence_system();      // my peer stores before the arrival mark of iter_end
+            if (PEERS && p.n_peers > 1) __threadfence_system();      // my peer stores before the arrival mark of iter_end
             named_bar_sync(GNN_BAR_MLP_ALL, TC_COMPUTE);
             if (tid == 0) iter_end(p, s_flag);
         }

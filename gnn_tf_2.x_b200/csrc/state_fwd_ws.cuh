@@ -155,7 +155,7 @@ static inline size_t ws_weight_floats(const NetLayout& lay) { return (size_t)ws_
 static inline size_t ws_smem_bytes(const NetLayout& lay, int ring, int capc, bool has_val) {
     size_t fl = ws_weight_floats(lay) + WS_MLP_GROUPS * (size_t)WS_TN * ws_tile_stride(lay.DP) + (size_t)ring * lay.DP + WS_ROWQ * 68 + WS_ROWQ * WS_TN +
                 WS_COLQ * (size_t)(capc + WS_COLPAD) + (has_val ? WS_ROWQ * (size_t)(capc + WS_COLPAD) : 0);   // weights, tiles x2, ring, row pointers / scales, arc sources, arc weights
-    return fl * 4;
+    return fl * 4 + 128;      // + alignment slack of the dynamic base
 }
 
 // bulk asynchronous copy global -> shared (UBLKCP): one thread, one instruction, any multiple of 16 bytes; both addresses
@@ -184,7 +184,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) state_iter_ws_kernel(const Iter
     const int CP = net.CP, capc = p.scol_cap, capb = capc + WS_COLPAD;
     const int nslot = p.ring_slots, slotcap = p.slot_rows;   // landing ring: nslot slots of slotcap rows, sub-tile j -> slot j % nslot
 
-    extern __shared__ __align__(16) float smem[];
+    // dynamic shared memory is only 16-byte aligned behind the static variables: the 128-byte rows of the ring want whole lines
+    extern __shared__ __align__(16) float smem_raw[];
+    float* smem = smem_raw + (((128u - ((unsigned)__cvta_generic_to_shared(smem_raw) & 127u)) & 127u) >> 2);
     constexpr int NT8 = DP / 8, NQ = DP / 16;           // n-tiles of 8 outputs; 16-column units of a state row
     constexpr int SAG = DP % 32 == 0 ? DP + 16 : DP;    // aggregate tile row stride (ws_tile_stride)
     const int CS = (CP + 7) / 8;                        // k-steps of the constant row

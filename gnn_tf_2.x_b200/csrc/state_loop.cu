@@ -20,6 +20,7 @@ struct IterProfile {
 };
 static IterProfile g_profile;
 static char g_last_kernel[96] = "";
+static char g_last_bwd_kernel[96] = "";
 
 struct DeviceInfo {
     int sms = 0, smem_optin = 0;
@@ -212,7 +213,7 @@ int make_plan(const gnn_graph* g, const gnn_mlp* net, const gnn_loop_args* a, Pl
         // tcgen05 variant: graphs with one weight per row ('sum' / 'average' / 'normalized' aggregation); GNN_B200_KERNEL=ws keeps the
         // mma.sync pipeline (comparison runs)
         const char* env = getenv("GNN_B200_KERNEL");
-        const bool tc = !plan->has_val && ks->iter_tc && !(env && !strcmp(env, "ws"));
+        const bool tc = !plan->has_val && ks->iter_tc[0] && !(env && !strcmp(env, "ws"));
         const bool bn_tr = a->training && lay.has_bn;
         // arc-index capacity per tile: 1.5x the average tile; the landing ring takes all the shared memory that is left
         // (at least 4 average sub-tiles, at most 4096 rows)
@@ -240,7 +241,7 @@ int make_plan(const gnn_graph* g, const gnn_mlp* net, const gnn_loop_args* a, Pl
         if (slots >= 8) {
             plan->ws = true;
             plan->tc = tc;
-            plan->kernel = tc ? ks->iter_tc : ks->iter_ws[plan->has_val ? 1 : 0];
+            plan->kernel = tc ? ks->iter_tc[a->n_global > 0 && a->n_peers > 1 ? 1 : 0] : ks->iter_ws[plan->has_val ? 1 : 0];
             plan->ts = TileShape{WS_TN, tc ? TC_THREADS : WS_THREADS};
             plan->scol_cap = capc;
             plan->ring_slots = slots;
@@ -416,6 +417,7 @@ extern "C" int gnn_state_loop_layout(const gnn_graph* g, const gnn_mlp* net, con
 }
 
 extern "C" const char* gnn_last_forward_kernel(void) { return g_last_kernel; }
+extern "C" const char* gnn_last_backward_kernel(void) { return g_last_bwd_kernel; }
 
 extern "C" int gnn_profile_iterations(int32_t enable) {
     if (enable && !g_profile.begin) {

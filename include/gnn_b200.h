@@ -215,6 +215,8 @@ int gnn_profile_iterations(int32_t enable);
 int gnn_profile_last_iterations(float* elapsed_ms, int32_t* launches);
 /* name of the iteration kernel the last gnn_state_loop_forward call launched ("" before the first call) */
 const char* gnn_last_forward_kernel(void);
+/* name of the node kernel the last gnn_state_loop_backward call launched ("" before the first call) */
+const char* gnn_last_backward_kernel(void);
 
 #ifdef __cplusplus
 }

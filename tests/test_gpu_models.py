@@ -177,14 +177,14 @@ def test_cuda_graph_training_step_equals_eager(problem):
     graphs = _toy_dataset(problem, n_graphs=18, seed=9)
     batches = [GraphTensor.fromGraphObject(b) for b in utils.getbatches(graphs, problem, 'average', batch_size=6)]
 
-    def one(layer, seed, **kw):
+    def one(index, seed, **kw):
         f_s, l_s = get_inout_dims('state', 3, 1, 2, problem, 0, None, **kw)
         f_o, l_o = get_inout_dims('output', 3, 1, 2, problem, 0, None, **kw)
         net_s = MLP(f_s, l_s, 'selu', 'lecun_normal', 'lecun_normal', dropout_rate=0.1, dropout_pos=0, batch_normalization=True, seed=seed)
         net_o = MLP(f_o, l_o, 'softmax', 'glorot_normal', 'glorot_normal', dropout_rate=0.1, dropout_pos=0, batch_normalization=False, seed=seed + 1)
         cls = {'n': GNNnodeBased, 'g': GNNgraphBased}[problem]
         return cls(net_s, net_o, Adam(learning_rate=0.01), categorical_crossentropy, {'from_logits': False}, state_vect_dim=0, max_iteration=5,
-                   threshold=0.01, addressed_problem='c', path_writer=f'/tmp/gnn_b200_graphed/{layer}/')
+                   threshold=0.01, addressed_problem='c', path_writer=f'/tmp/gnn_b200_graphed/{index}/')
 
     def make():
         if not lgnn: return one(0, 3)

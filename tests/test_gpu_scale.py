@@ -157,3 +157,56 @@ def test_lgnn_five_layers_matches_oracle(mode):
             got, want = grads[pos].cpu().numpy(), go2[li][j].numpy()
             assert rel_err(got, want) < TOL or float(np.max(np.abs(got - want))) < 1e-6, ('output', li, j)
             pos += 1
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# backward node kernel of state_bwd_l1.cuh (single Dense layer, no dropout, graphs that fill the GPU)
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('kw', [dict(DS=32, act='selu', bn=True, aggregation='average'),          # the C4 net, training BatchNormalization
+                                dict(DS=20, act='tanh', bn=False, aggregation='sum'),             # padded width 32, D = 20, no BN
+                                dict(DS=10, act='sigmoid', bn=True, aggregation='normalized'),    # padded width 16
+                                dict(DS=0, act='relu', bn=False, aggregation='average', NL=14, AL=3)],   # state = labels (C5 shape), width 16
+                         ids=['d32-selu-bn', 'd20-tanh', 'd10-sigmoid-bn', 'labels14-relu'])
+def test_pipelined_backward_kernel_matches_oracle_and_phased_kernel(kw, monkeypatch):
+    """ 12 345 nodes (not a multiple of the 128-node tile; more than 64 per SM, so the pipelined kernel is chosen): loss and BPTT
+    gradients against the oracle, and against the phase-structured kernel (GNN_B200_BWD=phased) on the same inputs """
+    _require_gpu()
+    from gnn_b200 import _native
+    from tests.parity import random_case, run_cuda, run_oracle, assert_parity
+    base = dict(seed=900, n_nodes=12345, n_arcs=70000, NL=3, AL=2, max_iter=4, threshold=0.0, weight_scale=None)
+    base.update(kw)
+    case = random_case(**base)
+    monkeypatch.delenv('GNN_B200_BWD', raising=False)
+    got = run_cuda(case, training=True)
+    assert _native.last_backward_kernel().startswith('state_bwd_node_l1_kernel'), _native.last_backward_kernel()
+    monkeypatch.setenv('GNN_B200_BWD', 'phased')
+    old = run_cuda(case, training=True)
+    assert _native.last_backward_kernel().startswith('state_bwd_node_kernel'), _native.last_backward_kernel()
+    want = run_oracle(case, training=True)
+    assert_parity(got, want, want64=lambda: run_oracle(case, training=True, float64=True))
+    assert got['k'] == old['k'] and got['loss'] == old['loss']          # same forward
+    for a, b in zip(got['gs'], old['gs']): assert rel_err(a, b) < 2e-5
+
+
+def test_pipelined_backward_kernel_label_gradients(monkeypatch):
+    """ gradients wrt node labels, arc labels and x0 (LGNN parallel / residual) through the pipelined kernel == phased kernel """
+    _require_gpu()
+    from gnn_b200 import _native
+    from gnn_b200.state_loop import state_loop, sparse_dense
+    from tests.parity import random_case, build_product
+    case = random_case(seed=901, n_nodes=11000, n_arcs=50000, NL=3, AL=2, DS=12, act='tanh', max_iter=3, threshold=0.0, masks=False)
+    g, gt, gnn = build_product(case)
+    probe = None
+    res = {}
+    for mode in ('pipelined', 'phased'):
+        if mode == 'phased': monkeypatch.setenv('GNN_B200_BWD', 'phased')
+        else: monkeypatch.delenv('GNN_B200_BWD', raising=False)
+        nodes = gt.nodes.clone().requires_grad_()
+        labels = gt.arcs[:, 2:].clone().requires_grad_()
+        x0 = torch.as_tensor(case['x0'], device='cuda').requires_grad_()
+        k, x = state_loop(gt.Adjacency, gnn.net_state, x0, nodes, sparse_dense(gt.Adjacency, nodes), sparse_dense(gt.ArcNode, labels),
+                          max_iteration=3, threshold=0.0, training=True)
+        if probe is None: probe = torch.as_tensor(np.random.default_rng(0).standard_normal(tuple(x.shape)).astype(np.float32), device='cuda')
+        res[mode] = [t.cpu().numpy() for t in torch.autograd.grad((x * probe).sum(), [nodes, labels, x0] + gnn.net_state.trainable_variables)]
+        assert _native.last_backward_kernel().startswith('state_bwd_node_l1_kernel' if mode == 'pipelined' else 'state_bwd_node_kernel')
+    for a, b in zip(res['pipelined'], res['phased']): assert rel_err(a, b) < 2e-5
