@@ -210,10 +210,12 @@ int make_plan(const gnn_graph* g, const gnn_mlp* net, const gnn_loop_args* a, Pl
     plan->ring_slots = plan->slot_rows = 0;
 
     if (ws_applicable(g, a, lay, di.sms) && ks->iter_ws[plan->has_val ? 1 : 0]) {
-        // tcgen05 variant: graphs with one weight per row ('sum' / 'average' / 'normalized' aggregation); GNN_B200_KERNEL=ws keeps the
-        // mma.sync pipeline (comparison runs)
+        // Two pipelines cover these graphs.  Measured on the same box with both shared-memory layouts aligned (C4, DP = 32): the
+        // mma.sync pipeline 0.222 / 0.196 ms per iteration (uniform / local sources), the tcgen05 pipeline 0.237 / 0.219 ms; equal on
+        // the C5 batches (DP = 16).  Node-range partition over 2 GPUs: 0.186 / 0.134 ms against 0.260 / 0.128 ms.  So the mma.sync
+        // pipeline is the planner's choice and the tcgen05 pipeline runs on request (GNN_B200_KERNEL=tc).
         const char* env = getenv("GNN_B200_KERNEL");
-        const bool tc = !plan->has_val && ks->iter_tc[0] && !(env && !strcmp(env, "ws"));
+        const bool tc = !plan->has_val && ks->iter_tc[0] && env && !strcmp(env, "tc");
         const bool bn_tr = a->training && lay.has_bn;
         // arc-index capacity per tile: 1.5x the average tile; the landing ring takes all the shared memory that is left
         // (at least 4 average sub-tiles, at most 4096 rows)

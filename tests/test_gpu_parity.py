@@ -368,10 +368,14 @@ def test_ws_and_symmetric_kernels_agree(monkeypatch):
     monkeypatch.setenv('GNN_B200_KERNEL', 'sym')
     b = run_cuda(case, training=False)
     assert _native.last_forward_kernel().startswith('state_iter_kernel<32,false')
-    monkeypatch.delenv('GNN_B200_KERNEL')
-    c = run_cuda(case, training=False)      # the planner's own choice at this size: the tcgen05 pipeline
+    monkeypatch.setenv('GNN_B200_KERNEL', 'tc')
+    c = run_cuda(case, training=False)      # the tcgen05 pipeline
     assert _native.last_forward_kernel() == 'state_iter_tc_kernel<32>'
     c2 = run_cuda(case, training=False)
+    monkeypatch.delenv('GNN_B200_KERNEL')
+    d = run_cuda(case, training=False)      # the planner's own choice at this size: the mma.sync pipeline (measured faster, state_loop.cu)
+    assert _native.last_forward_kernel() == 'state_iter_ws_kernel<32,false>'
+    np.testing.assert_array_equal(d['state'], a['state'])
     np.testing.assert_array_equal(c['state'], c2['state'])      # deterministic
     assert a['k'] == b['k'] == c['k']
     assert rel_err(a["state"], b["state"]) < 2e-5   # 3xTF32 tensor-core product vs sequential fp32 FMA

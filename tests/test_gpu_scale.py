@@ -38,19 +38,23 @@ def _c4(name):
     return bench, wl, gnn, GraphTensor.fromGraphObject(g, device='cuda')
 
 
-@pytest.mark.parametrize('name', ['c4u', 'c4l'])
-def test_c4_full_size_forward_and_training_parity(name):
-    """ the timed configuration itself: 1M nodes / 10M arcs / D = 32 -> the tcgen05 pipeline with the ring sized for this graph """
+@pytest.mark.parametrize('name,kernel', [('c4u', None), ('c4l', None), ('c4u', 'tc')])
+def test_c4_full_size_forward_and_training_parity(name, kernel, monkeypatch):
+    """ the timed configuration itself: 1M nodes / 10M arcs / D = 32 -> the pipelined kernel the planner picks (mma.sync pipeline), with
+    the ring sized for this graph, and the pipelined backward kernel; once more through the tcgen05 pipeline """
     _require_gpu()
     from gnn_b200 import _native
+    if kernel: monkeypatch.setenv('GNN_B200_KERNEL', kernel)
+    else: monkeypatch.delenv('GNN_B200_KERNEL', raising=False)
     bench, wl, gnn, gt = _c4(name)
     res = bench.parity_check(wl, gnn, gt, torch.device('cuda'), 2, training=False)
-    assert _native.last_forward_kernel() == 'state_iter_tc_kernel<32>'
+    assert _native.last_forward_kernel() == ('state_iter_tc_kernel<32>' if kernel == 'tc' else 'state_iter_ws_kernel<32,false>')
     assert res['k_equal'] and res['k'] == 2.0
     assert res['max_rel'] <= TOL, res
     assert res['elementwise_rel_p99'] <= TOL, res
     res = bench.parity_check(wl, gnn, gt, torch.device('cuda'), 2, training=True)
     assert res['ok'], res
+    assert _native.last_backward_kernel() == 'state_bwd_node_l1_kernel<32>'
 
 
 def _c5_batch(n_graphs, seed):
