@@ -139,7 +139,9 @@ class GraphPartition:
         if sorted_dst is None:
             sorted_dst = g._dst_sorted = bool(adj.col.shape[0] < 2 or np.all(adj.col[1:] >= adj.col[:-1]))
         if sorted_dst:
-            a0, a1 = int(np.searchsorted(adj.col, lo, side='left')), int(np.searchsorted(adj.col, hi, side='left'))
+            # (the bounds in the array's own dtype: a Python int makes numpy convert all E destinations to int64 first -- 13 ms per call at C4)
+            key = adj.col.dtype.type
+            a0, a1 = int(np.searchsorted(adj.col, key(lo), side='left')), int(np.searchsorted(adj.col, key(min(hi, np.iinfo(adj.col.dtype).max)), side='left'))
             n_mine = a1 - a0
             dst_loc = (up(adj.col[a0:a1], torch.int32) - lo).to(torch.int32)
             src_mine = up(adj.row[a0:a1], torch.int32)
