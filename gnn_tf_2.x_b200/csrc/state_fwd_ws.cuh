@@ -168,7 +168,9 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, int bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 
-template <int DP, bool HAS_VAL>
+// PEERS: node-range partition over several GPUs (rows other ranks gather from are also stored into their memory); a template
+// parameter so that the single-GPU kernel carries none of it (its MLP warps sit at the 128-register cap)
+template <int DP, bool HAS_VAL, bool PEERS>
 __global__ void __launch_bounds__(WS_THREADS, 1) state_iter_ws_kernel(const IterParams p) {
     constexpr int TN = WS_TN, LPN = DP / 4;
     constexpr int GPW = 32 / LPN;            // lane groups per warp = source rows per warp-wide cp.async
@@ -445,12 +447,16 @@ __global__ void __launch_bounds__(WS_THREADS, 1) state_iter_ws_kernel(const Iter
         // loaded ONE TILE OF THIS GROUP AHEAD (a whole tile period in flight)
         float4 xnext[2][NQ];
         float2 cnext[2][2];
+        uint32_t need_next = 0u;     // partition: peers that gather from my rows fg (bits 0-7) and fg + 8 (bits 8-15), fetched with the rows
+        const uint32_t others = PEERS ? (~(1u << p.rank) & ((1u << p.n_peers) - 1u) & 0xffu) : 0u;
         auto load_own = [&](long long tile) {
             const long long n0 = tile * TN;
+            if (PEERS) need_next = 0u;
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const long long n = n0 + 16 * mwarp + fg + 8 * h;
                 const bool valid = n < p.N;
+                if (PEERS && valid) need_next |= ((p.peer_mask ? __ldg(p.peer_mask + n) : 0xffu) & others) << (8 * h);
                 const float* xr = p.x_in + (size_t)(p.row_offset + n) * DP + 4 * ft;
                 const float* cr = p.cst + (size_t)n * CP + 2 * ft;
 #pragma unroll
@@ -469,6 +475,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) state_iter_ws_kernel(const Iter
             const int nvalid = (int)min((long long)TN, p.N - n0);
             float4 xcur[2][NQ];
             float2 ccur[2][2];
+            const uint32_t need_cur = need_next;
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
 #pragma unroll
@@ -559,7 +566,14 @@ __global__ void __launch_bounds__(WS_THREADS, 1) state_iter_ws_kernel(const Iter
                         for (int q = 0; q < NQ; ++q) {
                             const float4 y = make_float4(acc[2 * q][2 * h], acc[2 * q][2 * h + 1], acc[2 * q + 1][2 * h], acc[2 * q + 1][2 * h + 1]);
                             st4_hint(orow + 16 * q, y, stream_pol);
-                            if (p.n_peers > 1) store_to_peers(p, n0 + row, 16 * q + 4 * ft, y);
+                            if (PEERS) {       // the same 16 bytes into every peer that gathers from this row (mask fetched a tile ago)
+                                uint32_t nd = (need_cur >> (8 * h)) & 0xffu;
+                                while (nd) {
+                                    const int r = __ffs(nd) - 1;
+                                    nd &= nd - 1u;
+                                    st4(p.peer_out[r] + (size_t)(p.row_offset + n0 + row) * DP + 4 * ft + 16 * q, y);
+                                }
+                            }
                         }
                     }
                 }
@@ -626,7 +640,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) state_iter_ws_kernel(const Iter
             }
         } else {
             if (p.go_next && __any_sync(0xffffffffu, any_moving) && (tid & 31) == 0) s_flag = 1;
-            if (p.n_peers > 1) __threadfence_system();   // peer stores performed before the kernel is reported complete
+            if (PEERS && p.n_peers > 1) __threadfence_system();   // peer stores performed before the kernel is reported complete
             named_bar_sync(GNN_BAR_MLP_ALL, WS_MLP_ALL);
             if (tid == 0) iter_end(p, s_flag);
         }

@@ -14,10 +14,11 @@ const KernelSet* GNN_CAT(kernel_set_dp, GNN_DP)() {
         {{state_iter_kernel<GNN_DP, false, 128, 128>, state_iter_kernel<GNN_DP, true, 128, 128>},
          {state_iter_kernel<GNN_DP, false, 32, 32>, state_iter_kernel<GNN_DP, true, 32, 32>}},
 #if GNN_DP >= 16 && GNN_DP <= 32
-        {state_iter_ws_kernel<GNN_DP, false>, state_iter_ws_kernel<GNN_DP, true>},
+        {{state_iter_ws_kernel<GNN_DP, false, false>, state_iter_ws_kernel<GNN_DP, false, true>},
+         {state_iter_ws_kernel<GNN_DP, true, false>, state_iter_ws_kernel<GNN_DP, true, true>}},
         {state_iter_tc_kernel<GNN_DP, false>, state_iter_tc_kernel<GNN_DP, true>},
 #else
-        {nullptr, nullptr},
+        {{nullptr, nullptr}, {nullptr, nullptr}},
         {nullptr, nullptr},
 #endif
         {state_bwd_node_kernel<GNN_DP, 64, 128>, state_bwd_node_kernel<GNN_DP, 32, 32>},

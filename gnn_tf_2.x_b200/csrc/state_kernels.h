@@ -18,7 +18,7 @@ typedef void (*BnBwdReduceKernel)(const int*, int, const float*, const float*, c
 
 struct KernelSet {
     IterKernel iter[2][2];      // [tile: 0 = 128 nodes x 128 threads, 1 = 32 x 32][has_val]
-    IterKernel iter_ws[2];      // warp-specialised pipeline [has_val]; NULL when the width is not covered
+    IterKernel iter_ws[2][2];   // warp-specialised pipeline [has_val][node-range partition with peers]; NULL when the width is not covered
     IterKernel iter_tc[2];      // tcgen05 / tensor-memory pipeline (row-scale graphs) [node-range partition with peers]; NULL when the width is not covered
     BwdNodeKernel bwd_node[2];  // [tile: 0 = 64 nodes x 128 threads, 1 = 32 x 32]
     BwdNodeKernel bwd_node_l1;  // single Dense layer, no dropout: pipelined 128-node tiles (state_bwd_l1.cuh); NULL when the width is not covered

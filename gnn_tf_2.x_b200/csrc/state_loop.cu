@@ -209,7 +209,7 @@ int make_plan(const gnn_graph* g, const gnn_mlp* net, const gnn_loop_args* a, Pl
     plan->ws = plan->tc = false;
     plan->ring_slots = plan->slot_rows = 0;
 
-    if (ws_applicable(g, a, lay, di.sms) && ks->iter_ws[plan->has_val ? 1 : 0]) {
+    if (ws_applicable(g, a, lay, di.sms) && ks->iter_ws[plan->has_val ? 1 : 0][0]) {
         // Two pipelines cover these graphs.  Measured on the same box with both shared-memory layouts aligned (C4, DP = 32): the
         // mma.sync pipeline 0.222 / 0.196 ms per iteration (uniform / local sources), the tcgen05 pipeline 0.237 / 0.219 ms; equal on
         // the C5 batches (DP = 16).  Node-range partition over 2 GPUs: 0.186 / 0.134 ms against 0.260 / 0.128 ms.  So the mma.sync
@@ -243,7 +243,10 @@ int make_plan(const gnn_graph* g, const gnn_mlp* net, const gnn_loop_args* a, Pl
         if (slots >= 8) {
             plan->ws = true;
             plan->tc = tc;
-            plan->kernel = tc ? ks->iter_tc[a->n_global > 0 && a->n_peers > 1 ? 1 : 0] : ks->iter_ws[plan->has_val ? 1 : 0];
+            {
+                const int peers = a->n_global > 0 && a->n_peers > 1 ? 1 : 0;
+                plan->kernel = tc ? ks->iter_tc[peers] : ks->iter_ws[plan->has_val ? 1 : 0][peers];
+            }
             plan->ts = TileShape{WS_TN, tc ? TC_THREADS : WS_THREADS};
             plan->scol_cap = capc;
             plan->ring_slots = slots;

@@ -196,6 +196,9 @@ class GraphPartition:
         # allocation + rendezvous costs milliseconds and the loop calls are ordered on the stream anyway
         key = (str(self.device), id(self.group))
         cached = _SYMMETRIC_WORKSPACES.get(key)
+        # a repeated call of THIS partition object with a size it has already agreed on with the peers: every rank takes this branch
+        # together (same program, same objects), no collective and no host synchronisation
+        if cached is not None and self._ws is cached[0] and nbytes <= getattr(self, '_ws_agreed', -1): return self._ws
         need = torch.tensor([nbytes], dtype=torch.int64, device=self.device)
         dist.all_reduce(need, op=dist.ReduceOp.MAX, group=self.group)              # same decision on every rank
         if cached is None or cached[0].numel() < int(need.item()):
@@ -209,6 +212,7 @@ class GraphPartition:
                 return torch.empty(nbytes, dtype=torch.uint8, device=self.device)
         if self._ws is not cached[0]: self._state_offsets = None
         self._ws, self._handle = cached
+        self._ws_agreed = nbytes
         return self._ws
 
     def _signals(self, iters: int):
