@@ -89,7 +89,14 @@ class GNNnodeBased(BaseClass):
     @staticmethod
     def _save_net(net: Sequential, folder: str) -> None:
         os.makedirs(folder, exist_ok=True)
-        arch = [{'class': type(l).__name__, 'config': {k: v for k, v in l.config().items() if not callable(v)}} for l in net.layers]
+        arch = []
+        for l in net.layers:
+            cfg = l.config()
+            unsaved = [k for k, v in cfg.items() if callable(v)]
+            # the reference's Keras save keeps regularizers / initializers by config; a Python callable has none: refuse rather than
+            # silently write a model that loads without its regularisation
+            if unsaved: raise ValueError(f'cannot save layer {type(l).__name__}: {unsaved} are Python callables (pass them by name, or None)')
+            arch.append({'class': type(l).__name__, 'config': cfg})
         with open(os.path.join(folder, 'architecture.json'), 'w') as f:
             json.dump({'input_dim': net.input_dim, 'layers': arch}, f)
         np.savez(os.path.join(folder, 'weights.npz'), *net.get_weights())

@@ -4,6 +4,7 @@ import os
 import sys
 
 import numpy as np
+import pytest
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -82,3 +83,17 @@ def test_small_config_datasets():
     gid, coeff, G = b.nodegraph_segments()
     assert G == 40 and b.targets.shape == (40, 2) and b.nodes.shape[1] == 14 and b.arcs.shape[1] == 5
     assert np.all(b._dst[1:] >= 0) and abs(float(coeff.sum()) - 40.0) < 1e-3      # one unit of pooling weight per graph
+
+
+def test_save_refuses_python_callables(tmp_path):
+    """ a regularizer given as a Python callable has no serialisable config: save() raises instead of writing a model that would
+    load without it (the reference's Keras save keeps regularizers, GNN.py:93-111) """
+    from gnn_b200.keras_compat import Dense, Sequential
+    from gnn_b200.GNN import GNNnodeBased
+    net = Sequential([Dense(4, activation='tanh', kernel_regularizer=lambda w: (w * w).sum())], input_dim=6, device='cpu')
+    with pytest.raises(ValueError, match='callables'):
+        GNNnodeBased._save_net(net, str(tmp_path / 'net'))
+    plain = Sequential([Dense(4, activation='tanh')], input_dim=6, device='cpu')
+    GNNnodeBased._save_net(plain, str(tmp_path / 'plain'))
+    again = GNNnodeBased._load_net(str(tmp_path / 'plain'))
+    for a, b in zip(plain.get_weights(), again.get_weights()): np.testing.assert_array_equal(a, b)
