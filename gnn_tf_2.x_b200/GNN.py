@@ -191,6 +191,9 @@ class GNNnodeBased(BaseClass):
     def apply_filters(self, state_converged, nodes, adjacency, arcs_label, mask_index) -> torch.Tensor:
         """ [states] or [states|labels] of the nodes with output_mask AND set_mask (GNN.py:245-248) """
         if self.state_vect_dim: state_converged = torch.cat([state_converged, nodes], dim=1)
+        # every node selected (the index holds sorted, distinct positions: as many entries as rows = the identity): no gather, and no
+        # index_add in the backward (0.09 + 0.25 ms on the 1M-node graph)
+        if int(mask_index.shape[0]) == int(state_converged.shape[0]): return state_converged
         return state_converged.index_select(0, mask_index)
 
     def _next_seed(self):

@@ -231,6 +231,41 @@ class BatchNormalization(Layer):
     def config(self): return dict(momentum=self.momentum, epsilon=self.epsilon)
 
 
+class _TallDense(torch.autograd.Function):
+    """ ``x @ kernel + bias`` for MANY rows and few units (the output net of a million-node graph).  Forward as usual; in the
+    backward the weight gradient ``x^T g`` is a reduction over the rows, for which the library GEMM picks a split-K kernel
+    that runs at a few percent of the memory bandwidth (``sgemm_largek``: 1.4 ms for 1M x 35 against 2 output units, 3 % of a C4
+    training step and a third of a C5 one).  Here: partial products over blocks of 512 rows as ONE batched GEMM, then a sum over
+    the blocks -- a fixed order, so the result is deterministic, and more accurate than one long fp32 accumulation. """
+    BLOCK = 512
+
+    @staticmethod
+    def forward(ctx, x, kernel, bias):
+        ctx.save_for_backward(x, kernel)
+        return x @ kernel + bias
+
+    @staticmethod
+    def backward(ctx, g):
+        x, kernel = ctx.saved_tensors
+        g = g.contiguous()
+        gx = g @ kernel.t() if ctx.needs_input_grad[0] else None
+        gk = gb = None
+        if ctx.needs_input_grad[1]:
+            xc, S = x.contiguous(), _TallDense.BLOCK
+            n0 = (xc.shape[0] // S) * S
+            gk = torch.bmm(xc[:n0].view(-1, S, xc.shape[1]).transpose(1, 2), g[:n0].view(-1, S, g.shape[1])).sum(0)
+            if n0 < xc.shape[0]: gk = gk + xc[n0:].t() @ g[n0:]
+        if ctx.needs_input_grad[2]: gb = g.sum(0)
+        return gx, gk, gb
+
+
+def dense_affine(x: torch.Tensor, kernel: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
+    """ ``x @ kernel + bias``; tall inputs (>= 16 384 rows) take the block-wise weight gradient of _TallDense """
+    if x.dim() == 2 and x.shape[0] >= 16384 and torch.is_grad_enabled() and (kernel.requires_grad or bias.requires_grad or x.requires_grad):
+        return _TallDense.apply(x, kernel, bias)
+    return x @ kernel + bias
+
+
 #######################################################################################################################
 ## SEQUENTIAL #########################################################################################################
 #######################################################################################################################
@@ -332,7 +367,7 @@ class Sequential:
         seen = 0
         for layer in self.layers:
             if isinstance(layer, Dense):
-                x = apply_activation(layer.activation, x @ layer.kernel + layer.bias)
+                x = apply_activation(layer.activation, dense_affine(x, layer.kernel, layer.bias))
                 seen += 1
             elif isinstance(layer, Dropout):
                 if layer.alpha: raise NotImplementedError('AlphaDropout is not implemented on this path')

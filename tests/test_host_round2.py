@@ -97,3 +97,20 @@ def test_save_refuses_python_callables(tmp_path):
     GNNnodeBased._save_net(plain, str(tmp_path / 'plain'))
     again = GNNnodeBased._load_net(str(tmp_path / 'plain'))
     for a, b in zip(plain.get_weights(), again.get_weights()): np.testing.assert_array_equal(a, b)
+
+
+def test_tall_dense_gradients_equal_plain_autograd():
+    """ the block-wise weight gradient of the output net on tall inputs == torch's own (to rounding), same forward bit for bit """
+    torch.manual_seed(0)
+    x = torch.randn(20011, 35, requires_grad=True)
+    k, b = torch.randn(35, 2, requires_grad=True), torch.randn(2, requires_grad=True)
+    probe = torch.randn(20011, 2)
+    y1 = K.dense_affine(x, k, b)
+    assert type(y1.grad_fn).__name__ == '_TallDenseBackward'
+    y2 = x @ k + b
+    assert torch.equal(y1, y2)
+    g1 = torch.autograd.grad((y1 * probe).sum(), [x, k, b])
+    g2 = torch.autograd.grad((y2 * probe).sum(), [x, k, b])
+    for a, c in zip(g1, g2): assert torch.allclose(a, c, rtol=2e-5, atol=2e-4), float((a - c).abs().max())
+    small = K.dense_affine(torch.randn(100, 35, requires_grad=True), k, b)       # short inputs: the plain expression
+    assert type(small.grad_fn).__name__ != '_TallDenseBackward'
