@@ -16,7 +16,8 @@ import torch
 
 from .GNN_BaseClass import BaseClass
 from .graph_class import GraphObject, GraphTensor
-from .keras_compat import Sequential, Dense, losses as _losses, optimizers as _optimizers
+from . import _native
+from .keras_compat import Sequential, Dense, Dropout, losses as _losses, optimizers as _optimizers
 from .state_loop import state_loop, sparse_dense
 
 
@@ -241,9 +242,25 @@ class GNNnodeBased(BaseClass):
         state, node_self, aggregated_nodes, aggregated_arcs, labels = self._state_and_inputs(g)
         k, state = state_loop(g.Adjacency, self.net_state, state, node_self, aggregated_nodes, aggregated_arcs,
                               max_iteration=self.max_iteration, threshold=self.state_threshold, training=training, seed=seed)
-        net_in = self.apply_filters(state, g.nodes, g.Adjacency, labels, g.mask_index())
-        out = self.net_output(net_in, training=training, dropout_seed=seed, stream_base=16)
+        mask_index = g.mask_index()
+        out = self._output_one_pass(state, g.nodes, mask_index, training)
+        if out is None:
+            net_in = self.apply_filters(state, g.nodes, g.Adjacency, labels, mask_index)
+            out = self.net_output(net_in, training=training, dropout_seed=seed, stream_base=16)
         return k, state, out
+
+    def _output_one_pass(self, state, nodes, mask_index, training: bool):
+        """ inference, every node selected, output net = ONE Dense layer with at most 16 units (the reference's default output MLP
+        without its trailing BatchNormalization): act([state | labels] @ W + b) in one kernel of the library (gnn_output_dense)
+        instead of concat + GEMM + bias + softmax (GNN.py:245-248, 279).  None when it does not apply. """
+        if training or torch.is_grad_enabled() or state.device.type != 'cuda': return None
+        if type(self).apply_filters is not GNNnodeBased.apply_filters: return None
+        if int(mask_index.shape[0]) != int(state.shape[0]): return None
+        layers = [l for l in self.net_output.layers if not isinstance(l, Dropout)]        # Dropout is the identity in inference
+        if len(layers) != 1 or not isinstance(layers[0], Dense): return None
+        dense = layers[0]
+        if dense.units > 16 or dense.activation not in _native.ACT_CODES: return None
+        return _native.output_dense(state, nodes if self.state_vect_dim else None, dense.kernel, dense.bias, dense.activation)
 
 
 #######################################################################################################################

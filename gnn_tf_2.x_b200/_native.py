@@ -66,7 +66,7 @@ EXCHANGE_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int32, C.c_int64, C.c_int64)
 EXPORTED_SYMBOLS = ['gnn_last_error', 'gnn_abi_version', 'gnn_device_info', 'gnn_csr_build', 'gnn_spmm',
                     'gnn_state_loop_workspace_bytes', 'gnn_state_loop_layout', 'gnn_state_loop_forward', 'gnn_state_loop_backward',
                     'gnn_launch_count', 'gnn_profile_iterations', 'gnn_profile_last_iterations', 'gnn_last_forward_kernel',
-                    'gnn_last_backward_kernel']
+                    'gnn_last_backward_kernel', 'gnn_output_dense']
 
 
 def library_path() -> str: return _LIB_PATH
@@ -93,6 +93,8 @@ def lib() -> C.CDLL:
                                     C.POINTER(C.c_int32), C.c_void_p, C.POINTER(C.c_size_t), C.c_void_p]
         l.gnn_spmm.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32,
                                C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]
+        l.gnn_output_dense.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p,
+                                       C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
         l.gnn_state_loop_workspace_bytes.argtypes = [C.POINTER(gnn_graph), C.POINTER(gnn_mlp), C.POINTER(gnn_loop_args),
                                                      C.POINTER(C.c_size_t)]
         l.gnn_state_loop_layout.argtypes = [C.POINTER(gnn_graph), C.POINTER(gnn_mlp), C.POINTER(gnn_loop_args),
@@ -105,7 +107,7 @@ def lib() -> C.CDLL:
                                               C.c_void_p, C.c_size_t, C.c_void_p]
         l.gnn_profile_iterations.argtypes = [C.c_int32]
         l.gnn_profile_last_iterations.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_int32)]
-        for name in ('gnn_profile_iterations', 'gnn_profile_last_iterations', 'gnn_device_info', 'gnn_csr_build', 'gnn_spmm', 'gnn_state_loop_workspace_bytes',
+        for name in ('gnn_profile_iterations', 'gnn_profile_last_iterations', 'gnn_device_info', 'gnn_csr_build', 'gnn_spmm', 'gnn_output_dense', 'gnn_state_loop_workspace_bytes',
                      'gnn_state_loop_forward', 'gnn_state_loop_backward'):
             getattr(l, name).restype = C.c_int
         _lib = l
@@ -216,6 +218,24 @@ def spmm(rowptr: torch.Tensor, col: torch.Tensor, val: Optional[torch.Tensor], d
     with torch.cuda.device(device):
         check(l.gnn_spmm(_ptr(rowptr), _ptr(col), _ptr(val), n_rows, _ptr(dense), dense.stride(0) if F else 0, F, _ptr(out),
                          out.stride(0) if F else 0, 1 if accumulate else 0, _stream(device)), 'gnn_spmm')
+    return out
+
+
+def output_dense(x: Optional[torch.Tensor], labels: Optional[torch.Tensor], kernel: torch.Tensor, bias: torch.Tensor, activation: str) -> torch.Tensor:
+    """ act([x | labels] @ kernel + bias) in one pass over the rows (gnn_output_dense); inference only (no autograd) """
+    first = x if x is not None else labels
+    n, device = int(first.shape[0]), first.device
+    D = 0 if x is None else int(x.shape[1])
+    NL = 0 if labels is None else int(labels.shape[1])
+    T = int(kernel.shape[1])
+    if x is not None and x.stride(1) != 1: x = x.contiguous()
+    if labels is not None and labels.stride(1) != 1: labels = labels.contiguous()
+    kernel, bias = kernel.detach().contiguous(), bias.detach().contiguous()
+    out = torch.empty((n, T), dtype=torch.float32, device=device)
+    with torch.cuda.device(device):
+        check(lib().gnn_output_dense(_ptr(x) if D else None, n, D, x.stride(0) if D else 0, _ptr(labels) if NL else None, NL,
+                                     labels.stride(0) if NL else 0, _ptr(kernel), _ptr(bias), T, ACT_CODES[activation], _ptr(out),
+                                     _stream(device)), 'gnn_output_dense')
     return out
 
 

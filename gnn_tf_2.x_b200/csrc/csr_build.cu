@@ -224,6 +224,61 @@ __global__ void spmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* _
     for (int c = 0; c < 4; ++c)
         if (c < nc) dst[c] = accumulate ? dst[c] + acc[c] : acc[c];
 }
+
+// out[n, 0..T) = act([x[n, 0..D) | labels[n, 0..NL)] @ W[D + NL, T] + b): the output net of an inference Loop when it is one Dense layer
+// (GNN/GNN.py:275-279 with the reference's default output MLP).  Thread = row: weights in shared memory, the row is read once
+// (128-bit loads when the strides allow), softmax in registers -- one pass over the state instead of cat + GEMM + bias + softmax.
+constexpr int OUT_MAXT = 16;
+__global__ void output_dense_kernel(const float* __restrict__ x, long long n, int D, long long ldx, const float* __restrict__ labels, int NL,
+                                    long long ldl, const float* __restrict__ W, const float* __restrict__ b, int T, int act,
+                                    float* __restrict__ out) {
+    extern __shared__ float sw[];       // W [D + NL][T], b [T]
+    const int F = D + NL;
+    for (int i = threadIdx.x; i < F * T; i += blockDim.x) sw[i] = W[i];
+    for (int i = threadIdx.x; i < T; i += blockDim.x) sw[F * T + i] = b[i];
+    __syncthreads();
+    const long long row = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (row >= n) return;
+    float acc[OUT_MAXT];
+#pragma unroll
+    for (int o = 0; o < OUT_MAXT; ++o) acc[o] = o < T ? sw[F * T + o] : 0.f;
+    const float* xr = x + row * ldx;
+    const bool vec = (D % 4 == 0) && (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+    for (int j = 0; j < D; j += 4) {
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (vec) { const float4 q = ldg4(xr + j); v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w; }
+        else
+            for (int c = 0; c < 4; ++c) if (j + c < D) v[c] = __ldg(xr + j + c);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            if (j + c >= D) break;
+            const float* wr = sw + (size_t)(j + c) * T;
+#pragma unroll
+            for (int o = 0; o < OUT_MAXT; ++o) if (o < T) acc[o] = fmaf(v[c], wr[o], acc[o]);
+        }
+    }
+    for (int j = 0; j < NL; ++j) {
+        const float v = __ldg(labels + row * ldl + j);
+        const float* wr = sw + (size_t)(D + j) * T;
+#pragma unroll
+        for (int o = 0; o < OUT_MAXT; ++o) if (o < T) acc[o] = fmaf(v, wr[o], acc[o]);
+    }
+    if (act == GNN_ACT_SOFTMAX) {
+        float m = -INFINITY, sum = 0.f;
+#pragma unroll
+        for (int o = 0; o < OUT_MAXT; ++o) if (o < T) m = fmaxf(m, acc[o]);
+#pragma unroll
+        for (int o = 0; o < OUT_MAXT; ++o) if (o < T) { acc[o] = expf(acc[o] - m); sum += acc[o]; }
+        const float inv = 1.f / sum;
+#pragma unroll
+        for (int o = 0; o < OUT_MAXT; ++o) acc[o] *= inv;
+    } else {
+#pragma unroll
+        for (int o = 0; o < OUT_MAXT; ++o) acc[o] = act_apply(act, acc[o]);
+    }
+#pragma unroll
+    for (int o = 0; o < OUT_MAXT; ++o) if (o < T) out[row * T + o] = acc[o];
+}
 }  // namespace
 }  // namespace gnn
 
@@ -235,6 +290,21 @@ extern "C" int gnn_spmm(const int32_t* rowptr, const int32_t* col, const float* 
     if (!rowptr || !out) GNN_FAIL(GNN_ERR_INVALID, "gnn_spmm: NULL argument");  // col / dense may be NULL when there are no entries
     int64_t items = n_rows * ((F + 3) / 4);
     spmm_kernel<<<(unsigned)ceil_div(items, 256), 256, 0, stream>>>(rowptr, col, val, n_rows, dense, ld_dense, F, out, ld_out, accumulate);
+    GNN_LAUNCH_CHECK();
+    return GNN_OK;
+}
+
+extern "C" int gnn_output_dense(const float* x, int64_t n_rows, int32_t D, int64_t ld_x, const float* labels, int32_t NL, int64_t ld_labels,
+                                const float* W, const float* b, int32_t T, int32_t act, float* out, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (n_rows < 0 || D < 0 || NL < 0 || D + NL < 1 || T < 1) GNN_FAIL(GNN_ERR_INVALID, "gnn_output_dense: bad sizes");
+    if (T > gnn::OUT_MAXT) GNN_FAIL(GNN_ERR_UNSUPPORTED, "gnn_output_dense: at most %d output units", gnn::OUT_MAXT);
+    if (act < GNN_ACT_LINEAR || act > GNN_ACT_SOFTPLUS) GNN_FAIL(GNN_ERR_INVALID, "gnn_output_dense: unknown activation %d", act);
+    if (n_rows == 0) return GNN_OK;
+    if ((D > 0 && !x) || (NL > 0 && !labels) || !W || !b || !out) GNN_FAIL(GNN_ERR_INVALID, "gnn_output_dense: NULL argument");
+    const size_t smem = ((size_t)(D + NL) * T + T) * sizeof(float);
+    if (smem > 48 * 1024) GNN_FAIL(GNN_ERR_UNSUPPORTED, "gnn_output_dense: %zu bytes of weights do not fit", smem);
+    gnn::output_dense_kernel<<<(unsigned)ceil_div(n_rows, 256), 256, smem, stream>>>(x, n_rows, D, ld_x, labels, NL, ld_labels, W, b, T, act, out);
     GNN_LAUNCH_CHECK();
     return GNN_OK;
 }

@@ -213,6 +213,12 @@ int64_t gnn_launch_count(int32_t reset);
  * iteration launches enqueued between the two events (launches that found the loop stopped return at once). */
 int gnn_profile_iterations(int32_t enable);
 int gnn_profile_last_iterations(float* elapsed_ms, int32_t* launches);
+/* out[n_rows, T] = act([x[n_rows, D] | labels[n_rows, NL]] @ W[D + NL, T] + b[T]) : the output net of an inference Loop when it is ONE
+ * Dense layer over every node (replaces the tf.concat + Keras call of GNN/GNN.py:245-248, 279).  Row-major, ld_* in floats; W in
+ * Keras order (input x output); act = GNN_ACT_* incl. softmax; T <= 16.  Enqueues one kernel on the stream. */
+int gnn_output_dense(const float* x, int64_t n_rows, int32_t D, int64_t ld_x, const float* labels, int32_t NL, int64_t ld_labels,
+                     const float* W, const float* b, int32_t T, int32_t act, float* out, void* stream);
+
 /* name of the iteration kernel the last gnn_state_loop_forward call launched ("" before the first call) */
 const char* gnn_last_forward_kernel(void);
 /* name of the node kernel the last gnn_state_loop_backward call launched ("" before the first call) */

@@ -380,3 +380,24 @@ def test_ws_and_symmetric_kernels_agree(monkeypatch):
     assert a['k'] == b['k'] == c['k']
     assert rel_err(a["state"], b["state"]) < 2e-5   # 3xTF32 tensor-core product vs sequential fp32 FMA
     assert rel_err(c["state"], b["state"]) < 2e-5   # same, tcgen05
+
+
+@pytest.mark.parametrize('kw', [dict(DS=32, out_act='softmax', T=2), dict(DS=0, out_act='tanh', T=3), dict(DS=5, out_act='sigmoid', T=16),
+                                dict(DS=7, out_act='softmax', T=4, masks=True)],
+                         ids=['d32-softmax2', 'labels-tanh3', 'd5-sigmoid16', 'masked-falls-back'])
+def test_output_net_one_pass_equals_torch_path(kw):
+    """ inference Loop: the one-kernel output net (gnn_output_dense: every node selected, one Dense layer) against the torch path the
+    same Loop takes with autograd enabled, and against the oracle """
+    _require_gpu()
+    base = dict(seed=820, n_nodes=5000, n_arcs=30000, NL=3, AL=2, act='tanh', max_iter=4, threshold=0.0, masks=False)
+    base.update(kw)
+    case = random_case(**base)
+    g, gt, gnn = build_product(case)
+    with torch.no_grad():
+        k1, x1, out1 = gnn.Loop(gt, training=False, seed=case['seed'])
+    k2, x2, out2 = gnn.Loop(gt, training=False, seed=case['seed'])          # autograd on: concat + Dense through torch
+    assert float(k1) == float(k2) and torch.equal(x1, x2)
+    assert out1.shape == out2.shape
+    assert rel_err(out1.cpu().numpy(), out2.detach().cpu().numpy()) < 2e-6
+    want = run_oracle(case, training=False)
+    assert rel_err(out1.cpu().numpy(), want['out']) < TOL
