@@ -4,10 +4,10 @@
 //
 //   one persistent CTA per SM, 128-node tiles, three shared-memory stages, 20 warps in three roles joined by mbarriers (no
 //   block-wide barrier inside the tile loop):
-//     warps 16-19  producers: the input rows u_t = [x_t | A x_t | cst] of a tile land in the stage by cp.async; dL/dx_{t+1} and
-//                  y_t come through registers, delta = dL/dy * act'(y) (through the BatchNormalization backward when training) is
-//                  formed on the way and stored next to them; db = column sums of delta stay in the producers' registers.  They
-//                  run up to two tiles ahead of the arithmetic;
+//     warps 16-19  producers: all five inputs of a tile (u_t = [x_t | A x_t | cst], dL/dx_{t+1}, y_t) land in shared memory by cp.async
+//                  one tile ahead; delta = dL/dy * act'(y) (through the BatchNormalization backward when training) is then formed in
+//                  place; db = column sums of delta stay in the producers' registers.  They run up to two tiles ahead of the
+//                  arithmetic;
 //     warps 0-7    dW += u^T delta : warp w owns nodes 16 w .. 16 w + 15 of every tile; lane (kb, jb) keeps an 8 x 8 block of the
 //                  [2 DP x DP] gradient (+ its share of the constant rows) in REGISTERS for the whole kernel -- 5 shared-memory
 //                  loads per 36 packed FMA (fma.rn.f32x2), nothing is reduced per tile;
@@ -40,7 +40,7 @@ static inline int bwd_l1_su(const NetLayout& lay) { return odd_quad_stride(lay.K
 static inline int bwd_l1_sd(const NetLayout& lay) { return odd_quad_stride(lay.DP); }
 static inline size_t bwd_l1_stage_floats(const NetLayout& lay) { return (size_t)BL_TN * (bwd_l1_su(lay) + bwd_l1_sd(lay)); }
 static inline size_t bwd_l1_smem_bytes(const NetLayout& lay) {
-    return ((size_t)lay.DP * lay.KP + BL_STAGES * bwd_l1_stage_floats(lay)) * 4;
+    return ((size_t)lay.DP * lay.KP + BL_STAGES * bwd_l1_stage_floats(lay) + 2 * (size_t)BL_TN * lay.DP) * 4;   // W^T, stages, y_t of two tiles
 }
 static inline bool bwd_l1_applicable(const NetLayout& lay, bool training, bool y_saved) {
     if (lay.L != 1 || !y_saved || (lay.DP != 16 && lay.DP != 32) || lay.CP > BL_CROWS) return false;
@@ -79,12 +79,13 @@ static __global__ void __launch_bounds__(BL_NT, 1) state_bwd_node_l1_kernel(cons
     float* sWt = smem;                          // [DP][KP] transposed weights
     float* stage0 = sWt + DP * KP;              // [NS] x { U [TN][SU] | delta [TN][SD] }
     const size_t STAGE = (size_t)TN * (SU + SD);
+    float* ybuf = stage0 + NS * STAGE;          // [2][TN][DP]: y_t of the tile being formed and of the next one
     __shared__ __align__(8) uint64_t bar_full[NS], bar_empty[NS];
 
     for (int i = tid * 4; i < DP * KP; i += BL_NT * 4) st4(sWt + i, ldg4(p.wpack + net.wt_off[0] + i));
     if (tid == 0) {
-        // full: every producer thread arrives twice (its cp.async rows have landed; its delta pieces are stored); empty: one lane per compute warp
-        for (int i = 0; i < NS; ++i) { mbar_init(&bar_full[i], 2 * BL_PRODUCE); mbar_init(&bar_empty[i], BL_COMPUTE / 32); }
+        // full: every producer thread arrives once (its copies have landed and its delta pieces are stored); empty: one lane per compute warp
+        for (int i = 0; i < NS; ++i) { mbar_init(&bar_full[i], BL_PRODUCE); mbar_init(&bar_empty[i], BL_COMPUTE / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -109,59 +110,64 @@ static __global__ void __launch_bounds__(BL_NT, 1) state_bwd_node_l1_kernel(cons
             bnc[3][c] = bn_train ? p.bn_sums[j] : 0.f;
             bnc[4][c] = bn_train ? p.bn_sums[DP + j] : 0.f;
         }
+        // All five inputs of a tile travel by cp.async, ONE TILE AHEAD of the delta formation: u_t = [x_t | A x_t | cst] into the stage,
+        // dL/dx_{t+1} into the delta columns of the stage (delta is formed in place), y_t into a two-tile scratch.  A thread forms
+        // delta exactly for the pieces it copied itself, so cp.async.wait_group on its own groups is all the ordering it needs; the
+        // mbarrier arrive (release) then publishes copies and delta to the arithmetic warps.  (Loading dL/dx and y through
+        // registers inside the tile exposed one DRAM latency per tile: 4.9 us per tile whatever the width.)
+        auto issue = [&](int it) {
+            const int s = it % NS;
+            float* U = stage0 + (size_t)s * STAGE;
+            float* Dl = U + TN * SU;
+            float* Yb = ybuf + (size_t)(it & 1) * TN * DP;
+            const long long n0 = ((long long)blockIdx.x + (long long)it * gridDim.x) * TN;
+            const int nvalid = (int)min((long long)TN, p.N - n0);
+            for (int item = pt; item < TN * LPN; item += BL_PRODUCE) {
+                const int i = item / LPN;
+                const bool ok = i < nvalid;
+                const size_t off = (size_t)(n0 + (ok ? i : 0)) * DP + 4 * lig;
+                cp_async16_zfill(U + i * SU + 4 * lig, p.x_t + off, ok);
+                cp_async16_zfill(U + i * SU + DP + 4 * lig, p.agg_t + off, ok);
+                cp_async16_zfill(Dl + i * SD + 4 * lig, p.G + off, ok);
+                cp_async16_zfill(Yb + i * DP + 4 * lig, p.y_t + off, ok);
+            }
+            for (int item = pt; item < TN * CQ; item += BL_PRODUCE) {
+                const int i = item / CQ, c = item % CQ;
+                const bool ok = i < nvalid;
+                cp_async16_zfill(U + i * SU + 2 * DP + 4 * c, p.cst + (size_t)(n0 + (ok ? i : 0)) * CP + 4 * c, ok);
+            }
+            cp_async_commit();
+        };
         auto form = [&](auto act_c) {
             constexpr int ACT = decltype(act_c)::value;
+            if (my_tiles > 0) issue(0);
             for (int it = 0; it < my_tiles; ++it) {
                 const int s = it % NS;
-                if (it >= NS) mbar_wait<64>(&bar_empty[s], ((it / NS) - 1) & 1);
-                float* U = stage0 + (size_t)s * STAGE;
-                float* Dl = U + TN * SU;
+                if (it + 1 < my_tiles) {
+                    if (it + 1 >= NS) mbar_wait<64>(&bar_empty[(it + 1) % NS], (((it + 1) / NS) - 1) & 1);
+                    issue(it + 1);
+                    cp_async_wait_group<1>();       // my copies of tile it have landed (those of tile it + 1 stay in flight)
+                } else {
+                    cp_async_wait_group<0>();
+                }
+                float* Dl = stage0 + (size_t)s * STAGE + TN * SU;
+                const float* Yb = ybuf + (size_t)(it & 1) * TN * DP;
                 const long long n0 = ((long long)blockIdx.x + (long long)it * gridDim.x) * TN;
                 const int nvalid = (int)min((long long)TN, p.N - n0);
-                // the input rows of the tile: asynchronous copies straight into the stage
                 for (int item = pt; item < TN * LPN; item += BL_PRODUCE) {
                     const int i = item / LPN;
-                    const bool ok = i < nvalid;
-                    const size_t off = (size_t)(n0 + (ok ? i : 0)) * DP + 4 * lig;
-                    cp_async16_zfill(U + i * SU + 4 * lig, p.x_t + off, ok);
-                    cp_async16_zfill(U + i * SU + DP + 4 * lig, p.agg_t + off, ok);
-                }
-                for (int item = pt; item < TN * CQ; item += BL_PRODUCE) {
-                    const int i = item / CQ, c = item % CQ;
-                    const bool ok = i < nvalid;
-                    cp_async16_zfill(U + i * SU + 2 * DP + 4 * c, p.cst + (size_t)(n0 + (ok ? i : 0)) * CP + 4 * c, ok);
-                }
-                cp_async_mbar_arrive(&bar_full[s]);
-                // dL/dx_{t+1} and y_t of my pieces through registers, 4 pieces (8 loads) at a time: delta on the way into the stage
-                constexpr int NP = TN * LPN / BL_PRODUCE, NB = 4;
-                static_assert(NP % NB == 0, "pieces per producer thread");
-#pragma unroll 1
-                for (int q0 = 0; q0 < NP; q0 += NB) {
-                    float4 g4[NB], y4[NB];
+                    const float4 g4 = ld4(Dl + i * SD + 4 * lig), y4 = ld4(Yb + i * DP + 4 * lig);
+                    const float gg[4] = {g4.x, g4.y, g4.z, g4.w}, yy[4] = {y4.x, y4.y, y4.z, y4.w};
+                    float r[4];
 #pragma unroll
-                    for (int q = 0; q < NB; ++q) {
-                        const int i = (pt + (q0 + q) * BL_PRODUCE) / LPN;
-                        g4[q] = y4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (i < nvalid) {
-                            g4[q] = ldg4(p.G + (size_t)(n0 + i) * DP + 4 * lig);
-                            y4[q] = ldg4(p.y_t + (size_t)(n0 + i) * DP + 4 * lig);
-                        }
+                    for (int c = 0; c < 4; ++c) {
+                        // training BN: dL/dh = a (G - mean(G) - xhat mean(G xhat)),  xhat = (h - mean) / std;  otherwise the final affine a
+                        const float xhat = (yy[c] - bnc[0][c]) * bnc[1][c];
+                        const float gy = bnc[2][c] * (gg[c] - bnc[3][c] - xhat * bnc[4][c]);
+                        r[c] = (i < nvalid && 4 * lig + c < D) ? gy * act_grad_from_output(ACT, yy[c]) : 0.f;
+                        dbacc[c] += r[c];
                     }
-#pragma unroll
-                    for (int q = 0; q < NB; ++q) {
-                        const int i = (pt + (q0 + q) * BL_PRODUCE) / LPN;
-                        const float gg[4] = {g4[q].x, g4[q].y, g4[q].z, g4[q].w}, yy[4] = {y4[q].x, y4[q].y, y4[q].z, y4[q].w};
-                        float r[4];
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            // training BN: dL/dh = a (G - mean(G) - xhat mean(G xhat)),  xhat = (h - mean) / std;  otherwise the final affine a
-                            const float xhat = (yy[c] - bnc[0][c]) * bnc[1][c];
-                            const float gy = bnc[2][c] * (gg[c] - bnc[3][c] - xhat * bnc[4][c]);
-                            r[c] = (i < nvalid && 4 * lig + c < D) ? gy * act_grad_from_output(ACT, yy[c]) : 0.f;
-                            dbacc[c] += r[c];
-                        }
-                        st4(Dl + i * SD + 4 * lig, make_float4(r[0], r[1], r[2], r[3]));
-                    }
+                    st4(Dl + i * SD + 4 * lig, make_float4(r[0], r[1], r[2], r[3]));
                 }
                 mbar_arrive(&bar_full[s]);
             }
