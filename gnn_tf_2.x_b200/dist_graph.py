@@ -326,7 +326,7 @@ def bench_partitioned(g_host, wl, build_gnn, args, device, rank, world, with_e2e
     _native.launch_count(reset=True)
     warm = max(3, args.warmup)
     ms_fwd = timed(fwd, args.steps, warm)
-    launches = _native.launch_count() * args.steps // (args.steps + warm)
+    launches = _native.launch_count() // (args.steps + warm)          # library kernels per step (one partitioned loop), as at N = 1
     k_fwd = float(ks[-1])
 
     halo = part.halo.bytes_received_per_exchange(128) if part.halo is not None else 0
