@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define GNN_B200_ABI_VERSION 5
+#define GNN_B200_ABI_VERSION 6
 #define GNN_MAX_LAYERS 4 /* Dense layers per MLP */
 #define GNN_MAX_PEERS 8  /* GPUs of one NVSwitch domain */
 

@@ -120,7 +120,7 @@ def test_native_library_exports_every_declared_symbol():
     assert declared == set(_native.EXPORTED_SYMBOLS)
     lib = _native.lib()
     for name in declared: assert hasattr(lib, name), name
-    assert lib.gnn_abi_version() == 5
+    assert lib.gnn_abi_version() == 6
 
 
 def test_no_cpu_fallback():
