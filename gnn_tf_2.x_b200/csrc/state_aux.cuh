@@ -134,38 +134,49 @@ static __global__ void bn_stats_kernel(const int* __restrict__ go_cur, const dou
     stats[j] = mean; stats[DP + j] = var; stats[2 * DP + j] = a; stats[3 * DP + j] = c;
 }
 
-// x_{t+1} = a*h + c, convergence test against x_t (training-mode BatchNormalization only)
+// x_{t+1} = a*h + c, convergence test against x_t (training-mode BatchNormalization only).
+// BN_APPLY_U 16-byte pieces per thread, all loads first: twice the bytes in flight per thread of the one-piece version.
+constexpr int BN_APPLY_U = 2;
 template <int DP>
 static __global__ void bn_apply_kernel(const int* __restrict__ go_cur, int* __restrict__ go_next, int* __restrict__ k_ptr, int t,
                                 const float* __restrict__ h, const float* __restrict__ x_old, const float* __restrict__ stats,
                                 long long N, float thr, float* __restrict__ x_new) {
     if (*reinterpret_cast<const volatile int*>(go_cur) == 0) return;
     constexpr int LPN = DP / 4;
-    const long long item = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    const long long n = item / LPN;
-    const int lig = (int)(item % LPN);
-    const bool valid = n < N;
-    float d2 = 0.f, o2 = 0.f;
-    if (valid) {
-        const float4 hv = ldg4(h + n * DP + 4 * lig);
-        const float4 a = ldg4(stats + 2 * DP + 4 * lig), c = ldg4(stats + 3 * DP + 4 * lig);
-        const float4 xo = ldg4(x_old + n * DP + 4 * lig);
-        const float4 xn = make_float4(fmaf(a.x, hv.x, c.x), fmaf(a.y, hv.y, c.y), fmaf(a.z, hv.z, c.z), fmaf(a.w, hv.w, c.w));
-        st4(x_new + n * DP + 4 * lig, xn);
-        const float dx = xn.x - xo.x, dy = xn.y - xo.y, dz = xn.z - xo.z, dw = xn.w - xo.w;
-        d2 = dx * dx + dy * dy + dz * dz + dw * dw;
-        o2 = xo.x * xo.x + xo.y * xo.y + xo.z * xo.z + xo.w * xo.w;
-    }
+    const long long base = blockIdx.x * (long long)(blockDim.x * BN_APPLY_U) + threadIdx.x;
+    const int lig = (int)(base % LPN);       // blockDim.x is a multiple of LPN: the same columns for every piece of this thread
+    const float4 a = ldg4(stats + 2 * DP + 4 * lig), c = ldg4(stats + 3 * DP + 4 * lig);
+    float4 hv[BN_APPLY_U], xo[BN_APPLY_U];
+    long long node[BN_APPLY_U];
 #pragma unroll
-    for (int off = LPN / 2; off > 0; off >>= 1) {
-        d2 += __shfl_xor_sync(0xffffffffu, d2, off);
-        o2 += __shfl_xor_sync(0xffffffffu, o2, off);
+    for (int u = 0; u < BN_APPLY_U; ++u) {
+        node[u] = (base + (long long)u * blockDim.x) / LPN;
+        hv[u] = xo[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (node[u] < N) {
+            hv[u] = ldg4(h + node[u] * DP + 4 * lig);
+            xo[u] = ldg4(x_old + node[u] * DP + 4 * lig);
+        }
     }
-    const bool moving = valid && (sqrtf(d2) > thr * sqrtf(o2));
+    bool moving = false;
+#pragma unroll
+    for (int u = 0; u < BN_APPLY_U; ++u) {
+        const bool valid = node[u] < N;
+        const float4 xn = make_float4(fmaf(a.x, hv[u].x, c.x), fmaf(a.y, hv[u].y, c.y), fmaf(a.z, hv[u].z, c.z), fmaf(a.w, hv[u].w, c.w));
+        if (valid) st4(x_new + node[u] * DP + 4 * lig, xn);
+        const float dx = xn.x - xo[u].x, dy = xn.y - xo[u].y, dz = xn.z - xo[u].z, dw = xn.w - xo[u].w;
+        float d2 = valid ? dx * dx + dy * dy + dz * dz + dw * dw : 0.f;
+        float o2 = valid ? xo[u].x * xo[u].x + xo[u].y * xo[u].y + xo[u].z * xo[u].z + xo[u].w * xo[u].w : 0.f;
+#pragma unroll
+        for (int off = LPN / 2; off > 0; off >>= 1) {
+            d2 += __shfl_xor_sync(0xffffffffu, d2, off);
+            o2 += __shfl_xor_sync(0xffffffffu, o2, off);
+        }
+        moving |= valid && (sqrtf(d2) > thr * sqrtf(o2));
+    }
     // one atomic per CTA at most, and none once the flag is up (every CTA hitting one address serialises in L2)
     const int block_moving = __syncthreads_or(moving ? 1 : 0);
     if (go_next && block_moving && threadIdx.x == 0 && *reinterpret_cast<volatile int*>(go_next) == 0) atomicOr(go_next, 1);
-    if (item == 0) *k_ptr = t + 1;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *k_ptr = t + 1;
 }
 
 // x_out[N, D] = iterate number k (un-padded); k_out = (float) k

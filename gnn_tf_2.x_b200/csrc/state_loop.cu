@@ -395,7 +395,7 @@ extern "C" int gnn_state_loop_forward(const gnn_graph* g, const gnn_mlp* net, co
                                                                   net->bn_momentum, stats);
             GNN_LAUNCH_CHECK();
             const long long items = N * (lay.DP / 4);
-            bn_apply<<<(unsigned)ceil_div(items, 256), 256, 0, stream>>>(go + t, p.go_next, kptr, t, p.x_out, x_in, stats, N, a->threshold, x_next);
+            bn_apply<<<(unsigned)ceil_div(items, 256 * BN_APPLY_U), 256, 0, stream>>>(go + t, p.go_next, kptr, t, p.x_out, x_in, stats, N, a->threshold, x_next);
             GNN_LAUNCH_CHECK();
         }
     }
