@@ -180,6 +180,7 @@ static __global__ void bn_apply_kernel(const int* __restrict__ go_cur, int* __re
 }
 
 // x_out[N, D] = iterate number k (un-padded); k_out = (float) k
+constexpr int FINALIZE_U = 4;
 static __global__ void finalize_kernel(const int* __restrict__ k_ptr, const float* __restrict__ base, long long slab_floats,
                                 int ring /* 0: slab index = k, else k % ring */, long long N, int D, int DP,
                                 float* __restrict__ x_out, float* __restrict__ k_out) {
@@ -187,8 +188,20 @@ static __global__ void finalize_kernel(const int* __restrict__ k_ptr, const floa
     const float* src = base + (size_t)(ring ? (k % ring) : k) * slab_floats;
     const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (idx == 0 && k_out) *k_out = (float)k;
-    if (D == DP) {                                  // no padding: 128-bit copy (4 elements per thread)
-        if (4 * idx < N * D) st4(x_out + 4 * idx, ldg4(src + 4 * idx));
+    if (D == DP) {                                  // no padding: 128-bit copies, FINALIZE_U pieces per thread (all loads first)
+        const long long pieces = N * D / 4;
+        const long long first = blockIdx.x * (long long)(blockDim.x * FINALIZE_U) + threadIdx.x;
+        float4 v[FINALIZE_U];
+#pragma unroll
+        for (int u = 0; u < FINALIZE_U; ++u) {
+            const long long q = first + (long long)u * blockDim.x;
+            if (q < pieces) v[u] = ldg4(src + 4 * q);
+        }
+#pragma unroll
+        for (int u = 0; u < FINALIZE_U; ++u) {
+            const long long q = first + (long long)u * blockDim.x;
+            if (q < pieces) st4(x_out + 4 * q, v[u]);
+        }
         return;
     }
     if (idx >= N * D) return;

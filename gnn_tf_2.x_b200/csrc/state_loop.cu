@@ -403,7 +403,9 @@ extern "C" int gnn_state_loop_forward(const gnn_graph* g, const gnn_mlp* net, co
         GNN_CUDA(cudaEventRecord(g_profile.end, stream));
         g_profile.pending = true;
     }
-    finalize_kernel<<<(unsigned)ceil_div(std::max<long long>(NGLOB * lay.D, 1), 256), 256, 0, stream>>>(
+    // (no padding: 16-byte pieces, FINALIZE_U per thread; otherwise one element per thread)
+    const long long fin_items = lay.D == lay.DP ? ceil_div(NGLOB * lay.D / 4, (long long)FINALIZE_U) : NGLOB * lay.D;
+    finalize_kernel<<<(unsigned)ceil_div(std::max<long long>(fin_items, 1), 256), 256, 0, stream>>>(
         kptr, w.X, (long long)w.slab, save ? 0 : 2, NGLOB, lay.D, lay.DP, a->x_out, a->k_out);
     GNN_LAUNCH_CHECK();
     return GNN_OK;
