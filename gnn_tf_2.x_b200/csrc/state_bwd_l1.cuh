@@ -13,12 +13,14 @@
 //                  loads per 36 packed FMA (fma.rn.f32x2), nothing is reduced per tile;
 //     warps 8-15   g_u = delta W^T : thread = (two nodes, one quarter of the 2 DP columns): 16 columns of g_self or g_agg of its
 //                  two nodes in registers, W^T rows broadcast from shared memory, whole 32-byte sectors stored;
-//   register budgets per role through setmaxnreg (128 / 80 / 40; the pools are per SM sub-partition: 2 + 2 + 1 warps each);
+//   register budgets per role through setmaxnreg (128 / 80 / 64; the pools are per SM sub-partition: 2 + 2 + 1 warps each);
 //   at the end the eight register copies of dW and the db pieces are added in a fixed order (deterministic) into the CTA's
 //   partial slot.
 //
-// History (measured on the C4 graph, 1M nodes): phase-structured kernel of state_bwd.cuh 544 us; this arithmetic with block-wide
-// barriers between load / delta / arithmetic phases 352 us (half of the time in the phases around the two FMA loops);
+// History (measured on the C4 graph, 1M nodes, per launch): phase-structured kernel of state_bwd.cuh 544 us; this arithmetic with
+// block-wide barriers between load / delta / arithmetic phases 352 us (half of the time in the phases around the two FMA loops);
+// producer warps + mbarriers 255 us (FMA pipe 61 % busy); inputs by cp.async one tile ahead: little more at DP = 32, 35 % off at
+// DP = 16 (C5 batches), where a tile is too short to hide a DRAM latency.
 #pragma once
 #include "state_bwd.cuh"
 #include "state_fwd_ws.cuh"
