@@ -235,6 +235,7 @@ __global__ void spmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* _
 // of the instructions and the kernel took 246 us.
 constexpr int OUT_MAXT = 16;
 constexpr int OUT_LPR = 8;
+constexpr int OUT_RPG = 8;      // rows per lane group and block (OUT_ROWS_PER_LANE_GROUP)
 template <int MAXT>
 __global__ void output_dense_kernel(const float* __restrict__ x, long long n, int D, long long ldx, const float* __restrict__ labels, int NL,
                                     long long ldl, const float* __restrict__ W, const float* __restrict__ b, int T, int act,
@@ -244,8 +245,10 @@ __global__ void output_dense_kernel(const float* __restrict__ x, long long n, in
     for (int i = threadIdx.x; i < F * T; i += blockDim.x) sw[i] = W[i];
     for (int i = threadIdx.x; i < T; i += blockDim.x) sw[F * T + i] = b[i];
     __syncthreads();
-    const long long row = (blockIdx.x * (long long)blockDim.x + threadIdx.x) / OUT_LPR;
     const int l = threadIdx.x % OUT_LPR;
+    // OUT_ROWS_PER_LANE_GROUP rows per lane group, one after the other: the weights are staged once per 256 rows, not once per 32
+    for (int rr = 0; rr < OUT_RPG; ++rr) {
+    const long long row = (blockIdx.x * (long long)OUT_RPG + rr) * (blockDim.x / OUT_LPR) + threadIdx.x / OUT_LPR;
     const bool valid = row < n;
     float acc[MAXT];
 #pragma unroll
@@ -284,7 +287,7 @@ __global__ void output_dense_kernel(const float* __restrict__ x, long long n, in
 #pragma unroll
         for (int o = 0; o < MAXT; ++o)
             if (o < T) acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], off);      // (T is uniform: every lane takes the same branch)
-    if (!valid || l != 0) return;
+    if (!valid || l != 0) continue;
 #pragma unroll
     for (int o = 0; o < MAXT; ++o) if (o < T) acc[o] += sw[F * T + o];
     if (act == GNN_ACT_SOFTMAX) {
@@ -302,6 +305,7 @@ __global__ void output_dense_kernel(const float* __restrict__ x, long long n, in
     }
 #pragma unroll
     for (int o = 0; o < MAXT; ++o) if (o < T) out[row * T + o] = acc[o];
+    }
 }
 }  // namespace
 }  // namespace gnn
@@ -328,7 +332,7 @@ extern "C" int gnn_output_dense(const float* x, int64_t n_rows, int32_t D, int64
     if ((D > 0 && !x) || (NL > 0 && !labels) || !W || !b || !out) GNN_FAIL(GNN_ERR_INVALID, "gnn_output_dense: NULL argument");
     const size_t smem = ((size_t)(D + NL) * T + T) * sizeof(float);
     if (smem > 48 * 1024) GNN_FAIL(GNN_ERR_UNSUPPORTED, "gnn_output_dense: %zu bytes of weights do not fit", smem);
-    const unsigned grid = (unsigned)ceil_div(n_rows * gnn::OUT_LPR, 256);
+    const unsigned grid = (unsigned)ceil_div(n_rows, (256 / gnn::OUT_LPR) * gnn::OUT_RPG);
     if (T <= 2) gnn::output_dense_kernel<2><<<grid, 256, smem, stream>>>(x, n_rows, D, ld_x, labels, NL, ld_labels, W, b, T, act, out);
     else if (T <= 4) gnn::output_dense_kernel<4><<<grid, 256, smem, stream>>>(x, n_rows, D, ld_x, labels, NL, ld_labels, W, b, T, act, out);
     else if (T <= 8) gnn::output_dense_kernel<8><<<grid, 256, smem, stream>>>(x, n_rows, D, ld_x, labels, NL, ld_labels, W, b, T, act, out);
